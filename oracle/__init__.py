@@ -27,4 +27,4 @@ from .postproc import (  # noqa: F401
     set_anchors, safe_exp, interpret_output, batch_iou, nms,
     filter_prediction,
 )
-from .nets import forward, NET_BUILDERS, layer_table  # noqa: F401
+from .nets import forward, NET_BUILDERS, layer_table, param_specs  # noqa: F401

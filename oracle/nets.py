@@ -126,14 +126,14 @@ def _resnet50(t, x, n_out):
       first = blk == 'a'
       stride = 2 if (first and down) else 1
       b2 = scope + 'res%s_branch2/res%s_branch2' % (unit, unit)
-      y = t.conv_bn(b2 + 'a', x, mid, 1, stride, relu=True)
-      y = t.conv_bn(b2 + 'b', y, mid, 3, 1, relu=True)
-      y = t.conv_bn(b2 + 'c', y, out, 1, 1, relu=False)
-      if first:
+      if first:     # branch1 is built first in the reference (resnet50_convDet.py:49-54)
         sc = t.conv_bn(scope + 'res%s_branch1' % unit, x, out, 1, stride,
                        relu=False)
       else:
         sc = x
+      y = t.conv_bn(b2 + 'a', x, mid, 1, stride, relu=True)
+      y = t.conv_bn(b2 + 'b', y, mid, 3, 1, relu=True)
+      y = t.conv_bn(b2 + 'c', y, out, 1, 1, relu=False)
       x = t._rec('res' + unit, 'add_relu', S.relu(sc + y))
   return t.conv('conv5', x, n_out, 3, 1, 'SAME', relu=False)
 
@@ -154,14 +154,20 @@ def forward(net, weights, images, n_out=72, dtype=np.float32, keep=None):
   return NET_BUILDERS[net](t, x, n_out)
 
 
-def layer_table(net, height, width, n_out=72):
+def layer_table(net, height, width, n_out=72, specs=None):
   """(name, kind, out_shape, flops, params) per layer on a 1-pixel-cheap trace:
-  geometry is computed analytically (no arithmetic on real-size tensors)."""
+  geometry is computed analytically (no arithmetic on real-size tensors).
+  `specs`: optional list filled with (param_name, shape) in reference order."""
   rows = []
+  if specs is None:
+    specs = []
 
   class T:
     def conv(self, name, x, filters, size, stride, padding='SAME', relu=True):
       h, w, c = x
+      if not getattr(self, '_bn', False):
+        specs.append((name + '/kernels', (size, size, c, filters)))
+        specs.append((name + '/biases', (filters,)))
       ho = S.conv_geometry(h, size, stride, padding)[0]
       wo = S.conv_geometry(w, size, stride, padding)[0]
       rows.append((name, 'conv', (ho, wo, filters),
@@ -171,7 +177,14 @@ def layer_table(net, height, width, n_out=72):
 
     def conv_bn(self, scope, x, filters, size, stride, relu=True, bias=False,
                 eps=1e-5):
-      return self.conv(scope, x, filters, size, stride, 'SAME', relu)
+      specs.append((scope + '/kernels', (size, size, x[2], filters)))
+      for leaf in (['biases'] if bias else []) + ['gamma', 'beta', 'mean', 'var']:
+        specs.append((scope + '/' + leaf, (filters,)))
+      self._bn = True
+      try:
+        return self.conv(scope, x, filters, size, stride, 'SAME', relu)
+      finally:
+        self._bn = False
 
     def pool(self, name, x, size, stride, padding='SAME'):
       h, w, c = x
@@ -210,3 +223,10 @@ def layer_table(net, height, width, n_out=72):
   finally:
     S.relu = orig_relu
   return rows
+
+
+def param_specs(net, n_out=72):
+  """[(reference variable name, shape)] in the order of model.model_params."""
+  specs = []
+  layer_table(net, 375, 1242, n_out, specs)
+  return specs

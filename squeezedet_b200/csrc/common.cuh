@@ -1,0 +1,70 @@
+// Shared declarations for libsqdet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/sqdet_b200.h"
+
+namespace sqdet {
+
+// ---- error plumbing (nothing throws across the C ABI) ---------------------------------
+void set_error(const std::string& msg);
+int  fail(int code, const std::string& msg);
+int  cuda_fail(cudaError_t err, const char* what);
+
+#define SQ_CUDA(expr)                                                   \
+  do {                                                                  \
+    cudaError_t _e = (expr);                                            \
+    if (_e != cudaSuccess) return ::sqdet::cuda_fail(_e, #expr);        \
+  } while (0)
+
+#define SQ_CHECK_LAUNCH(what)                                           \
+  do {                                                                  \
+    cudaError_t _e = cudaGetLastError();                                \
+    if (_e != cudaSuccess) return ::sqdet::cuda_fail(_e, what);         \
+  } while (0)
+
+// ---- TF NHWC geometry (tf.nn.conv2d / tf.nn.max_pool) ------------------
+struct Geom {
+  int out, pad_before, pad_after;
+};
+inline Geom tf_geometry(int in, int k, int stride, int padding) {
+  Geom g;
+  if (padding == SQDET_PAD_SAME) {
+    g.out = (in + stride - 1) / stride;
+    int total = (g.out - 1) * stride + k - in;
+    if (total < 0) total = 0;
+    g.pad_before = total / 2;
+    g.pad_after = total - g.pad_before;
+  } else {
+    g.out = (in - k) / stride + 1;
+    g.pad_before = g.pad_after = 0;
+  }
+  return g;
+}
+
+// ---- kernel launchers (each returns a status; asynchronous on `stream`) ----------------
+struct ConvArgs {
+  const float* x;       // [B,H,W,Cin]
+  const float* w;       // [kh,kw,Cin,Cout] (HWIO)
+  const float* bias;    // [Cout] or null
+  const float* scale;   // [Cout] or null   (frozen BN: rsqrt(var+eps)*gamma)
+  const float* shift;   // [Cout] or null   (beta - mean*scale)
+  float* y;             // [B,Ho,Wo,y_cstride], this conv owns channels [y_coff, y_coff+Cout)
+  int B, H, W, Cin, Cout, size, stride, padding, relu, y_cstride, y_coff;
+};
+int launch_conv_simt(const ConvArgs& a, cudaStream_t stream);
+
+int launch_maxpool(const float* x, float* y, int B, int H, int W, int C, int size,
+                   int stride, int padding, cudaStream_t stream);
+int launch_add_relu(const float* a, const float* b, float* y, int64_t n, cudaStream_t stream);
+
+int launch_interpret(const float* preds, const float* anchors, float* boxes, float* probs,
+                     int64_t* cls, int B, int grid_h, int grid_w, int K, int C,
+                     int image_width, int image_height, float exp_thresh,
+                     cudaStream_t stream);
+int launch_topk_nms(const float* boxes, const float* probs, const int64_t* cls, int B,
+                    int A, int classes, int top_n, float prob_thresh, float nms_thresh,
+                    sqdet_det* dets, int32_t* counts, int max_dets, cudaStream_t stream);
+
+}  // namespace sqdet

@@ -1,0 +1,935 @@
+// libsqdet_b200 engine: graph builder, parameter store, executor and the C ABI.
+//
+// The reference's "framework" for this path is the TF-1.0 graph that the nets build
+// through ModelSkeleton's layer constructors and run through sess.run
+// (src/nn_skeleton.py:74-135, 374-586; src/nets/*.py; src/demo.py:193-199).  Here the
+// Python facade records the same constructor calls into a plan (sqdet_add_*), and this
+// file owns everything behind it: shape inference with TF geometry, activation and
+// weight storage in HBM, BN folding to (scale, shift), kernel selection per op
+// (tcgen05 3xTF32 implicit GEMM or fp32 SIMT), CUDA-graph capture of the whole forward,
+// and the fused post-processing.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace sqdet {
+
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t err, const char* what) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(err) + " in " + what;
+  return SQDET_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------
+struct Tensor {
+  std::string name;
+  int B = 0, H = 0, W = 0, C = 0;
+  float* dev = nullptr;         // owned (except tensor 0 when the caller feeds its own)
+  bool external = false;
+  int64_t numel() const { return (int64_t)B * H * W * C; }
+};
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  std::vector<float> host;
+  float* dev = nullptr;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+enum OpKind { OP_CONV, OP_POOL, OP_FIRE, OP_ADD_RELU };
+
+struct ConvSpec {
+  std::string name;
+  int src = -1, dst = -1;
+  int Cin = 0, Cout = 0, size = 1, stride = 1, padding = SQDET_PAD_SAME, relu = 1;
+  int y_coff = 0;
+  int p_kernel = -1, p_bias = -1, p_gamma = -1, p_beta = -1, p_mean = -1, p_var = -1;
+  float* scale = nullptr;      // device, BN only
+  float* shift = nullptr;
+  TcConvPlan tc;               // tensor-core plan (valid when tc.enabled)
+};
+
+struct Op {
+  OpKind kind;
+  std::string name;
+  std::vector<ConvSpec> convs;   // 1 for conv, 3 for fire (squeeze, expand1x1, expand3x3)
+  int src = -1, src2 = -1, dst = -1;
+  int size = 0, stride = 0, padding = 0;
+  int64_t flops = 0, params = 0, min_bytes = 0;
+  int launches = 0;
+  TcFirePlan tcfire;             // fused expand pair (valid when tcfire.enabled)
+};
+
+}  // namespace sqdet
+
+using namespace sqdet;
+
+struct sqdet_engine {
+  sqdet_config cfg;
+  int device = 0;
+  bool finalized = false;
+  bool params_dirty = true;
+  std::vector<Tensor> tensors;
+  std::vector<Param> params;
+  std::map<std::string, int> param_index;
+  std::vector<Op> ops;
+  int preds = -1;
+  int grid_h = 0, grid_w = 0;
+  int64_t num_anchors = 0;
+  std::vector<double> anchors_f64;
+  float* d_anchors = nullptr;
+  float* d_boxes = nullptr;
+  float* d_probs = nullptr;
+  int64_t* d_cls = nullptr;
+  sqdet_det* d_dets = nullptr;
+  int32_t* d_counts = nullptr;
+  int max_dets = 0;
+  float* d_input = nullptr;       // engine-owned input buffer (host-path + graph)
+  // CUDA graph of one forward, keyed by (input pointer, stream)
+  cudaGraphExec_t graph_exec = nullptr;
+  const float* graph_input = nullptr;
+  cudaStream_t graph_stream = nullptr;
+  bool use_graph = true;
+  cudaStream_t own_stream = nullptr;
+  std::vector<cudaEvent_t> prof_events;
+};
+
+namespace sqdet {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+static int add_param(sqdet_engine* e, const std::string& name, std::vector<int64_t> shape) {
+  auto it = e->param_index.find(name);
+  if (it != e->param_index.end()) return it->second;
+  Param p;
+  p.name = name;
+  p.shape = std::move(shape);
+  p.host.assign((size_t)p.numel(), 0.f);
+  e->params.push_back(std::move(p));
+  const int idx = (int)e->params.size() - 1;
+  e->param_index[name] = idx;
+  return idx;
+}
+
+static int new_tensor(sqdet_engine* e, const std::string& name, int B, int H, int W, int C) {
+  Tensor t;
+  t.name = name;
+  t.B = B; t.H = H; t.W = W; t.C = C;
+  e->tensors.push_back(t);
+  return (int)e->tensors.size() - 1;
+}
+
+static int check_build(sqdet_engine* e, int src) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  if (e->finalized) return fail(SQDET_ERR_STATE, "graph is frozen (already finalized)");
+  if (src < 0 || src >= (int)e->tensors.size())
+    return fail(SQDET_ERR_INVALID_ARG, "unknown source tensor id");
+  return SQDET_OK;
+}
+
+// Describe one convolution reading tensor `src`; output geometry by TF rules.
+static int make_conv(sqdet_engine* e, const std::string& name, int src, int filters, int size,
+                     int stride, int padding, int relu, bool bn, bool with_bias,
+                     ConvSpec* cs, int* Ho, int* Wo) {
+  if (filters <= 0 || size <= 0 || stride <= 0)
+    return fail(SQDET_ERR_INVALID_ARG, "conv '" + name + "': non-positive filters/size/stride");
+  if (padding != SQDET_PAD_SAME && padding != SQDET_PAD_VALID)
+    return fail(SQDET_ERR_INVALID_ARG, "conv '" + name + "': padding must be SAME(0) or VALID(1)");
+  const Tensor& in = e->tensors[src];
+  const Geom gh = tf_geometry(in.H, size, stride, padding);
+  const Geom gw = tf_geometry(in.W, size, stride, padding);
+  if (gh.out <= 0 || gw.out <= 0)
+    return fail(SQDET_ERR_INVALID_ARG, "conv '" + name + "': kernel larger than input");
+  cs->name = name;
+  cs->src = src;
+  cs->Cin = in.C;
+  cs->Cout = filters;
+  cs->size = size;
+  cs->stride = stride;
+  cs->padding = padding;
+  cs->relu = relu;
+  cs->p_kernel = add_param(e, name + "/kernels", {size, size, in.C, filters});
+  if (!bn || with_bias) cs->p_bias = add_param(e, name + "/biases", {filters});
+  if (bn) {
+    // reference order of model_params: kernels, [biases], gamma, beta, mean, var
+    cs->p_gamma = add_param(e, name + "/gamma", {filters});
+    cs->p_beta = add_param(e, name + "/beta", {filters});
+    cs->p_mean = add_param(e, name + "/mean", {filters});
+    cs->p_var = add_param(e, name + "/var", {filters});
+  }
+  *Ho = gh.out;
+  *Wo = gw.out;
+  return SQDET_OK;
+}
+
+static void conv_cost(const sqdet_engine* e, const ConvSpec& c, int Ho, int Wo, Op* op) {
+  const Tensor& in = e->tensors[c.src];
+  const int64_t px = (int64_t)in.B * Ho * Wo;
+  op->flops += 2LL * c.size * c.size * c.Cin * c.Cout * px;
+  op->params += (int64_t)(1 + c.size * c.size * c.Cin) * c.Cout;
+}
+
+static int run_conv(sqdet_engine* e, const ConvSpec& c, const float* x_override,
+                    cudaStream_t stream) {
+  const Tensor& in = e->tensors[c.src];
+  const Tensor& out = e->tensors[c.dst];
+  const float* x = (c.src == 0 && x_override) ? x_override : in.dev;
+  if (c.tc.enabled) return launch_conv_tc(c.tc, x, out.dev, stream);
+  ConvArgs a;
+  a.x = x;
+  a.w = e->params[c.p_kernel].dev;
+  a.bias = c.p_bias >= 0 ? e->params[c.p_bias].dev : nullptr;
+  a.scale = c.scale;
+  a.shift = c.shift;
+  a.y = out.dev;
+  a.B = in.B; a.H = in.H; a.W = in.W; a.Cin = c.Cin; a.Cout = c.Cout;
+  a.size = c.size; a.stride = c.stride; a.padding = c.padding; a.relu = c.relu;
+  a.y_cstride = out.C;
+  a.y_coff = c.y_coff;
+  return launch_conv_simt(a, stream);
+}
+
+static int run_op(sqdet_engine* e, const Op& op, const float* x_override, cudaStream_t stream) {
+  switch (op.kind) {
+    case OP_CONV:
+      return run_conv(e, op.convs[0], x_override, stream);
+    case OP_FIRE: {
+      int rc = run_conv(e, op.convs[0], x_override, stream);
+      if (rc) return rc;
+      if (op.tcfire.enabled)
+        return launch_fire_expand_tc(op.tcfire, e->tensors[op.convs[1].src].dev,
+                                     e->tensors[op.dst].dev, stream);
+      rc = run_conv(e, op.convs[1], nullptr, stream);
+      if (rc) return rc;
+      return run_conv(e, op.convs[2], nullptr, stream);
+    }
+    case OP_POOL: {
+      const Tensor& in = e->tensors[op.src];
+      const float* x = (op.src == 0 && x_override) ? x_override : in.dev;
+      return launch_maxpool(x, e->tensors[op.dst].dev, in.B, in.H, in.W, in.C, op.size,
+                            op.stride, op.padding, stream);
+    }
+    case OP_ADD_RELU: {
+      const Tensor& a = e->tensors[op.src];
+      return launch_add_relu(a.dev, e->tensors[op.src2].dev, e->tensors[op.dst].dev,
+                             a.numel(), stream);
+    }
+  }
+  return fail(SQDET_ERR_STATE, "unknown op kind");
+}
+
+static int run_postproc(sqdet_engine* e, cudaStream_t stream) {
+  const sqdet_config& c = e->cfg;
+  int rc = launch_interpret(e->tensors[e->preds].dev, e->d_anchors, e->d_boxes, e->d_probs,
+                            e->d_cls, c.batch_size, e->grid_h, e->grid_w, c.anchors_per_grid,
+                            c.classes, c.image_width, c.image_height, c.exp_thresh, stream);
+  if (rc) return rc;
+  return launch_topk_nms(e->d_boxes, e->d_probs, e->d_cls, c.batch_size, (int)e->num_anchors,
+                         c.classes, c.top_n_detection, c.prob_thresh, c.nms_thresh, e->d_dets,
+                         e->d_counts, e->max_dets, stream);
+}
+
+// Upload parameters and derive what the kernels consume (BN scale/shift, TC packs).
+static int prepare_params(sqdet_engine* e) {
+  if (!e->params_dirty) return SQDET_OK;
+  for (auto& p : e->params) {
+    if (!p.dev) SQ_CUDA(cudaMalloc(&p.dev, sizeof(float) * (size_t)p.numel()));
+    SQ_CUDA(cudaMemcpy(p.dev, p.host.data(), sizeof(float) * (size_t)p.numel(),
+                       cudaMemcpyHostToDevice));
+  }
+  for (auto& op : e->ops) {
+    for (auto& c : op.convs) {
+      if (c.p_gamma >= 0) {
+        // tf.nn.batch_normalization: inv = rsqrt(var+eps)*gamma; y = x*inv + (beta - mean*inv)
+        const int n = c.Cout;
+        std::vector<float> sc(n), sh(n);
+        const auto& g = e->params[c.p_gamma].host;
+        const auto& b = e->params[c.p_beta].host;
+        const auto& m = e->params[c.p_mean].host;
+        const auto& v = e->params[c.p_var].host;
+        for (int i = 0; i < n; ++i) {
+          const float inv = (1.0f / sqrtf(v[i] + e->cfg.batch_norm_epsilon)) * g[i];
+          sc[i] = inv;
+          sh[i] = b[i] - m[i] * inv;
+        }
+        if (!c.scale) SQ_CUDA(cudaMalloc(&c.scale, sizeof(float) * n));
+        if (!c.shift) SQ_CUDA(cudaMalloc(&c.shift, sizeof(float) * n));
+        SQ_CUDA(cudaMemcpy(c.scale, sc.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+        SQ_CUDA(cudaMemcpy(c.shift, sh.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+      }
+    }
+  }
+  // tensor-core weight packs
+  for (auto& op : e->ops) {
+    for (auto& c : op.convs) {
+      if (!c.tc.enabled) continue;
+      const float* bias = c.p_bias >= 0 ? e->params[c.p_bias].host.data() : nullptr;
+      int rc = tc_conv_pack_weights(&c.tc, e->params[c.p_kernel].host.data(), bias);
+      if (rc) return rc;
+    }
+    if (op.tcfire.enabled) {
+      const ConvSpec& e1 = op.convs[1];
+      const ConvSpec& e3 = op.convs[2];
+      int rc = tc_fire_pack_weights(&op.tcfire, e->params[e1.p_kernel].host.data(),
+                                    e->params[e1.p_bias].host.data(),
+                                    e->params[e3.p_kernel].host.data(),
+                                    e->params[e3.p_bias].host.data());
+      if (rc) return rc;
+    }
+  }
+  e->params_dirty = false;
+  // weights changed -> any captured graph still points at the same buffers, so it stays valid
+  return SQDET_OK;
+}
+
+static void drop_graph(sqdet_engine* e) {
+  if (e->graph_exec) {
+    cudaGraphExecDestroy(e->graph_exec);
+    e->graph_exec = nullptr;
+  }
+  e->graph_input = nullptr;
+  e->graph_stream = nullptr;
+}
+
+static int enqueue_all(sqdet_engine* e, const float* images_dev, cudaStream_t stream) {
+  for (const auto& op : e->ops) {
+    int rc = run_op(e, op, images_dev, stream);
+    if (rc) return rc;
+  }
+  return run_postproc(e, stream);
+}
+
+static int forward_impl(sqdet_engine* e, const float* images_dev, cudaStream_t stream) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_forward before sqdet_finalize");
+  if (!images_dev) return fail(SQDET_ERR_INVALID_ARG, "null images pointer");
+  DeviceGuard guard(e->device);
+  if (!guard.ok) return fail(SQDET_ERR_CUDA, "cannot select the engine's device");
+  int rc = prepare_params(e);
+  if (rc) return rc;
+  const bool can_graph = e->use_graph && stream != nullptr;   // legacy stream cannot capture
+  if (!can_graph) return enqueue_all(e, images_dev, stream);
+  if (!e->graph_exec || e->graph_input != images_dev || e->graph_stream != stream) {
+    drop_graph(e);
+    cudaGraph_t graph = nullptr;
+    SQ_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_all(e, images_dev, stream);
+    cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+    e->graph_input = images_dev;
+    e->graph_stream = stream;
+  }
+  SQ_CUDA(cudaGraphLaunch(e->graph_exec, stream));
+  return SQDET_OK;
+}
+
+}  // namespace sqdet
+
+// =========================================================================================
+//                                        C ABI
+// =========================================================================================
+extern "C" {
+
+const char* sqdet_last_error(void) { return g_last_error.c_str(); }
+const char* sqdet_version(void) { return "sqdet_b200 0.1 (sm_100a)"; }
+
+int sqdet_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int sqdet_create(const sqdet_config* cfg, int device, sqdet_engine** out) {
+  if (!cfg || !out) return fail(SQDET_ERR_INVALID_ARG, "sqdet_create: null argument");
+  if (cfg->batch_size <= 0 || cfg->image_height <= 0 || cfg->image_width <= 0)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_create: batch/image size must be positive");
+  if (cfg->classes <= 0 || cfg->anchors_per_grid <= 0)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_create: classes/anchors_per_grid must be positive");
+  if (cfg->math_mode != SQDET_MATH_FP32_SIMT && cfg->math_mode != SQDET_MATH_TF32X3_TC)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_create: unknown math_mode");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaGetDeviceCount (no CUDA device: this "
+                                              "library has no CPU fallback)");
+  if (device < 0 || device >= ndev)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_create: device index out of range");
+  cudaDeviceProp prop;
+  SQ_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SQDET_ERR_UNSUPPORTED, "sqdet_create: this build targets sm_100a (B200) only");
+  std::unique_ptr<sqdet_engine> e(new sqdet_engine());
+  e->cfg = *cfg;
+  e->device = device;
+  new_tensor(e.get(), "image_input", cfg->batch_size, cfg->image_height, cfg->image_width, 3);
+  *out = e.release();
+  return SQDET_OK;
+}
+
+int sqdet_destroy(sqdet_engine* e) {
+  if (!e) return SQDET_OK;
+  DeviceGuard guard(e->device);
+  drop_graph(e);
+  for (auto& t : e->tensors)
+    if (t.dev && !t.external) cudaFree(t.dev);
+  for (auto& p : e->params)
+    if (p.dev) cudaFree(p.dev);
+  for (auto& op : e->ops) {
+    for (auto& c : op.convs) {
+      if (c.scale) cudaFree(c.scale);
+      if (c.shift) cudaFree(c.shift);
+      tc_conv_release(&c.tc);
+    }
+    tc_fire_release(&op.tcfire);
+  }
+  cudaFree(e->d_anchors);
+  cudaFree(e->d_boxes);
+  cudaFree(e->d_probs);
+  cudaFree(e->d_cls);
+  cudaFree(e->d_dets);   // also owns d_counts (one blob)
+  cudaFree(e->d_input);
+  for (auto ev : e->prof_events) cudaEventDestroy(ev);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+  return SQDET_OK;
+}
+
+int sqdet_add_conv(sqdet_engine* e, const char* layer_name, int src, int filters, int size,
+                   int stride, int padding, int relu, int* out) {
+  int rc = check_build(e, src);
+  if (rc) return rc;
+  if (!layer_name || !out) return fail(SQDET_ERR_INVALID_ARG, "sqdet_add_conv: null argument");
+  Op op;
+  op.kind = OP_CONV;
+  op.name = layer_name;
+  ConvSpec cs;
+  int Ho, Wo;
+  rc = make_conv(e, layer_name, src, filters, size, stride, padding, relu, false, true, &cs,
+                 &Ho, &Wo);
+  if (rc) return rc;
+  cs.dst = new_tensor(e, layer_name, e->tensors[src].B, Ho, Wo, filters);
+  conv_cost(e, cs, Ho, Wo, &op);
+  op.src = src;
+  op.dst = cs.dst;
+  op.convs.push_back(cs);
+  e->ops.push_back(op);
+  *out = cs.dst;
+  return SQDET_OK;
+}
+
+int sqdet_add_conv_bn(sqdet_engine* e, const char* scope_name, int src, int filters, int size,
+                      int stride, int relu, int conv_with_bias, int* out) {
+  int rc = check_build(e, src);
+  if (rc) return rc;
+  if (!scope_name || !out) return fail(SQDET_ERR_INVALID_ARG, "sqdet_add_conv_bn: null argument");
+  Op op;
+  op.kind = OP_CONV;
+  op.name = scope_name;
+  ConvSpec cs;
+  int Ho, Wo;
+  rc = make_conv(e, scope_name, src, filters, size, stride, SQDET_PAD_SAME, relu, true,
+                 conv_with_bias != 0, &cs, &Ho, &Wo);
+  if (rc) return rc;
+  cs.dst = new_tensor(e, scope_name, e->tensors[src].B, Ho, Wo, filters);
+  conv_cost(e, cs, Ho, Wo, &op);
+  op.src = src;
+  op.dst = cs.dst;
+  op.convs.push_back(cs);
+  e->ops.push_back(op);
+  *out = cs.dst;
+  return SQDET_OK;
+}
+
+int sqdet_add_pool(sqdet_engine* e, const char* layer_name, int src, int size, int stride,
+                   int padding, int* out) {
+  int rc = check_build(e, src);
+  if (rc) return rc;
+  if (!layer_name || !out) return fail(SQDET_ERR_INVALID_ARG, "sqdet_add_pool: null argument");
+  if (size <= 0 || stride <= 0)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_add_pool: non-positive size/stride");
+  if (padding != SQDET_PAD_SAME && padding != SQDET_PAD_VALID)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_add_pool: padding must be SAME(0) or VALID(1)");
+  const Tensor in = e->tensors[src];
+  const Geom gh = tf_geometry(in.H, size, stride, padding);
+  const Geom gw = tf_geometry(in.W, size, stride, padding);
+  if (gh.out <= 0 || gw.out <= 0)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_add_pool: window larger than input");
+  Op op;
+  op.kind = OP_POOL;
+  op.name = layer_name;
+  op.src = src;
+  op.size = size;
+  op.stride = stride;
+  op.padding = padding;
+  op.dst = new_tensor(e, layer_name, in.B, gh.out, gw.out, in.C);
+  e->ops.push_back(op);
+  *out = op.dst;
+  return SQDET_OK;
+}
+
+int sqdet_add_fire(sqdet_engine* e, const char* layer_name, int src, int s1x1, int e1x1,
+                   int e3x3, int* out) {
+  int rc = check_build(e, src);
+  if (rc) return rc;
+  if (!layer_name || !out) return fail(SQDET_ERR_INVALID_ARG, "sqdet_add_fire: null argument");
+  const std::string base(layer_name);
+  Op op;
+  op.kind = OP_FIRE;
+  op.name = base;
+  ConvSpec sq, x1, x3;
+  int Ho, Wo;
+  rc = make_conv(e, base + "/squeeze1x1", src, s1x1, 1, 1, SQDET_PAD_SAME, 1, false, true, &sq,
+                 &Ho, &Wo);
+  if (rc) return rc;
+  sq.dst = new_tensor(e, base + "/squeeze1x1", e->tensors[src].B, Ho, Wo, s1x1);
+  conv_cost(e, sq, Ho, Wo, &op);
+  rc = make_conv(e, base + "/expand1x1", sq.dst, e1x1, 1, 1, SQDET_PAD_SAME, 1, false, true,
+                 &x1, &Ho, &Wo);
+  if (rc) return rc;
+  rc = make_conv(e, base + "/expand3x3", sq.dst, e3x3, 3, 1, SQDET_PAD_SAME, 1, false, true,
+                 &x3, &Ho, &Wo);
+  if (rc) return rc;
+  const int dst = new_tensor(e, base, e->tensors[src].B, Ho, Wo, e1x1 + e3x3);
+  x1.dst = dst; x1.y_coff = 0;
+  x3.dst = dst; x3.y_coff = e1x1;      // tf.concat([ex1x1, ex3x3], 3)  squeezeDet.py:106
+  conv_cost(e, x1, Ho, Wo, &op);
+  conv_cost(e, x3, Ho, Wo, &op);
+  op.src = src;
+  op.dst = dst;
+  op.convs = {sq, x1, x3};
+  e->ops.push_back(op);
+  *out = dst;
+  return SQDET_OK;
+}
+
+int sqdet_add_add_relu(sqdet_engine* e, const char* name, int a, int b, int* out) {
+  int rc = check_build(e, a);
+  if (rc) return rc;
+  rc = check_build(e, b);
+  if (rc) return rc;
+  if (!name || !out) return fail(SQDET_ERR_INVALID_ARG, "sqdet_add_add_relu: null argument");
+  const Tensor ta = e->tensors[a], tb = e->tensors[b];
+  if (ta.B != tb.B || ta.H != tb.H || ta.W != tb.W || ta.C != tb.C)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_add_add_relu: operand shapes differ");
+  Op op;
+  op.kind = OP_ADD_RELU;
+  op.name = name;
+  op.src = a;
+  op.src2 = b;
+  op.dst = new_tensor(e, name, ta.B, ta.H, ta.W, ta.C);
+  e->ops.push_back(op);
+  *out = op.dst;
+  return SQDET_OK;
+}
+
+int sqdet_set_preds(sqdet_engine* e, int preds, const double* anchor_box, int64_t num_anchors) {
+  int rc = check_build(e, preds);
+  if (rc) return rc;
+  if (!anchor_box) return fail(SQDET_ERR_INVALID_ARG, "sqdet_set_preds: null anchors");
+  const Tensor& t = e->tensors[preds];
+  const int K = e->cfg.anchors_per_grid, C = e->cfg.classes;
+  if (t.C != K * (C + 1 + 4))
+    return fail(SQDET_ERR_INVALID_ARG,
+                "sqdet_set_preds: preds must have ANCHOR_PER_GRID*(CLASSES+1+4) channels");
+  if (num_anchors != (int64_t)t.H * t.W * K)
+    return fail(SQDET_ERR_INVALID_ARG,
+                "sqdet_set_preds: len(ANCHOR_BOX) != grid_h*grid_w*ANCHOR_PER_GRID");
+  e->preds = preds;
+  e->grid_h = t.H;
+  e->grid_w = t.W;
+  e->num_anchors = num_anchors;
+  e->anchors_f64.assign(anchor_box, anchor_box + num_anchors * 4);
+  return SQDET_OK;
+}
+
+int sqdet_finalize(sqdet_engine* e) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  if (e->finalized) return fail(SQDET_ERR_STATE, "already finalized");
+  if (e->preds < 0) return fail(SQDET_ERR_STATE, "sqdet_finalize before sqdet_set_preds");
+  DeviceGuard guard(e->device);
+  if (!guard.ok) return fail(SQDET_ERR_CUDA, "cannot select the engine's device");
+  const sqdet_config& c = e->cfg;
+  // result capacity
+  const bool topn = c.top_n_detection > 0 && c.top_n_detection < e->num_anchors;
+  e->max_dets = c.max_dets > 0 ? c.max_dets : (topn ? c.top_n_detection : 1024);
+  if (topn && e->max_dets < c.top_n_detection)
+    return fail(SQDET_ERR_INVALID_ARG, "max_dets smaller than TOP_N_DETECTION");
+  if (topn && c.top_n_detection > 1024)
+    return fail(SQDET_ERR_UNSUPPORTED, "TOP_N_DETECTION above 1024 is not supported");
+  // activations
+  for (size_t i = 0; i < e->tensors.size(); ++i) {
+    Tensor& t = e->tensors[i];
+    SQ_CUDA(cudaMalloc(&t.dev, sizeof(float) * (size_t)t.numel()));
+  }
+  e->d_input = e->tensors[0].dev;
+  const int64_t A = e->num_anchors, B = c.batch_size;
+  std::vector<float> anc((size_t)A * 4);
+  for (size_t i = 0; i < anc.size(); ++i) anc[i] = (float)e->anchors_f64[i];   // fp64 -> fp32 cast
+  SQ_CUDA(cudaMalloc(&e->d_anchors, sizeof(float) * anc.size()));
+  SQ_CUDA(cudaMemcpy(e->d_anchors, anc.data(), sizeof(float) * anc.size(), cudaMemcpyHostToDevice));
+  SQ_CUDA(cudaMalloc(&e->d_boxes, sizeof(float) * (size_t)(B * A * 4)));
+  SQ_CUDA(cudaMalloc(&e->d_probs, sizeof(float) * (size_t)(B * A)));
+  SQ_CUDA(cudaMalloc(&e->d_cls, sizeof(int64_t) * (size_t)(B * A)));
+  // records and counts share ONE allocation: [B*max_dets records][B int32 counts] is the
+  // blob a rank contributes to the N-GPU all-gather (squeezedet_b200/shard.py).
+  {
+    const size_t rec_bytes = sizeof(sqdet_det) * (size_t)(B * e->max_dets);
+    void* blob = nullptr;
+    SQ_CUDA(cudaMalloc(&blob, rec_bytes + sizeof(int32_t) * (size_t)B));
+    e->d_dets = reinterpret_cast<sqdet_det*>(blob);
+    e->d_counts = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(blob) + rec_bytes);
+  }
+  SQ_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  // per-op accounting + tensor-core planning
+  for (auto& op : e->ops) {
+    int64_t bytes = 0;
+    op.launches = 0;
+    if (op.kind == OP_CONV || op.kind == OP_FIRE) {
+      bytes += 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.dst].numel() + 4 * op.params;
+      if (c.math_mode == SQDET_MATH_TF32X3_TC) {
+        if (op.kind == OP_CONV) {
+          ConvSpec& cs = op.convs[0];
+          int rc = tc_conv_plan(&cs.tc, e->tensors[cs.src].B, e->tensors[cs.src].H,
+                                e->tensors[cs.src].W, cs.Cin, cs.Cout, cs.size, cs.stride,
+                                cs.padding, cs.relu, cs.p_gamma >= 0, e->tensors[cs.dst].C,
+                                cs.y_coff, e->tensors[cs.src].dev, e->tensors[cs.dst].dev);
+          if (rc < 0) return rc;
+        } else {
+          ConvSpec& sq = op.convs[0];
+          int rc = tc_conv_plan(&sq.tc, e->tensors[sq.src].B, e->tensors[sq.src].H,
+                                e->tensors[sq.src].W, sq.Cin, sq.Cout, 1, 1, SQDET_PAD_SAME, 1,
+                                false, e->tensors[sq.dst].C, 0, e->tensors[sq.src].dev,
+                                e->tensors[sq.dst].dev);
+          if (rc < 0) return rc;
+          const Tensor& q = e->tensors[sq.dst];
+          rc = tc_fire_plan(&op.tcfire, q.B, q.H, q.W, q.C, op.convs[1].Cout, op.convs[2].Cout,
+                            q.dev, e->tensors[op.dst].dev);
+          if (rc < 0) return rc;
+        }
+      }
+      if (op.kind == OP_CONV) op.launches = 1;
+      else op.launches = 1 + (op.tcfire.enabled ? 1 : 2);
+    } else if (op.kind == OP_POOL) {
+      bytes = 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.dst].numel();
+      op.launches = 1;
+    } else {
+      bytes = 4 * 3 * e->tensors[op.dst].numel();
+      op.launches = 1;
+    }
+    op.min_bytes = bytes;
+  }
+  e->finalized = true;
+  e->params_dirty = true;
+  return SQDET_OK;
+}
+
+int sqdet_num_params(sqdet_engine* e) { return e ? (int)e->params.size() : SQDET_ERR_INVALID_ARG; }
+
+int sqdet_param_info(sqdet_engine* e, int index, char* name_buf, int name_cap, int64_t shape[4],
+                     int* ndim) {
+  if (!e || index < 0 || index >= (int)e->params.size())
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_param_info: bad index");
+  const Param& p = e->params[index];
+  if (name_buf && name_cap > 0) {
+    strncpy(name_buf, p.name.c_str(), (size_t)name_cap - 1);
+    name_buf[name_cap - 1] = 0;
+  }
+  if (shape)
+    for (int i = 0; i < 4; ++i) shape[i] = i < (int)p.shape.size() ? p.shape[i] : 1;
+  if (ndim) *ndim = (int)p.shape.size();
+  return SQDET_OK;
+}
+
+int sqdet_set_param(sqdet_engine* e, const char* name, const float* data, const int64_t* shape,
+                    int ndim) {
+  if (!e || !name || !data || !shape)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_set_param: null argument");
+  auto it = e->param_index.find(name);
+  if (it == e->param_index.end())
+    return fail(SQDET_ERR_NOT_FOUND, std::string("sqdet_set_param: no parameter named '") + name + "'");
+  Param& p = e->params[it->second];
+  bool same = ndim == (int)p.shape.size();
+  for (int i = 0; same && i < ndim; ++i) same = shape[i] == p.shape[i];
+  if (!same)
+    return fail(SQDET_ERR_INVALID_ARG,
+                std::string("sqdet_set_param: shape mismatch for '") + name + "'");
+  memcpy(p.host.data(), data, sizeof(float) * (size_t)p.numel());
+  e->params_dirty = true;
+  return SQDET_OK;
+}
+
+int sqdet_num_tensors(sqdet_engine* e) { return e ? (int)e->tensors.size() : SQDET_ERR_INVALID_ARG; }
+
+int sqdet_tensor_info(sqdet_engine* e, int id, char* name_buf, int name_cap, int64_t shape[4]) {
+  if (!e || id < 0 || id >= (int)e->tensors.size())
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_tensor_info: bad id");
+  const Tensor& t = e->tensors[id];
+  if (name_buf && name_cap > 0) {
+    strncpy(name_buf, t.name.c_str(), (size_t)name_cap - 1);
+    name_buf[name_cap - 1] = 0;
+  }
+  if (shape) { shape[0] = t.B; shape[1] = t.H; shape[2] = t.W; shape[3] = t.C; }
+  return SQDET_OK;
+}
+
+int sqdet_read_tensor(sqdet_engine* e, int id, float* host_out) {
+  if (!e || id < 0 || id >= (int)e->tensors.size() || !host_out)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_read_tensor: bad argument");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_read_tensor before sqdet_finalize");
+  DeviceGuard guard(e->device);
+  SQ_CUDA(cudaDeviceSynchronize());
+  const Tensor& t = e->tensors[id];
+  SQ_CUDA(cudaMemcpy(host_out, t.dev, sizeof(float) * (size_t)t.numel(), cudaMemcpyDeviceToHost));
+  return SQDET_OK;
+}
+
+int sqdet_num_ops(sqdet_engine* e) { return e ? (int)e->ops.size() + 2 : SQDET_ERR_INVALID_ARG; }
+
+int sqdet_op_info(sqdet_engine* e, int index, char* name_buf, int name_cap, int64_t* flops,
+                  int64_t* params, int64_t* min_bytes) {
+  if (!e || index < 0 || index >= (int)e->ops.size() + 2)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_op_info: bad index");
+  std::string name;
+  int64_t fl = 0, pa = 0, by = 0;
+  const int nops = (int)e->ops.size();
+  if (index < nops) {
+    const Op& op = e->ops[index];
+    name = op.name; fl = op.flops; pa = op.params; by = op.min_bytes;
+  } else {
+    const int64_t B = e->cfg.batch_size, A = e->num_anchors;
+    if (index == nops) {
+      name = "interpret_output";
+      by = e->preds >= 0 ? 4 * e->tensors[e->preds].numel() + B * A * (16 + 4 + 8) : 0;
+    } else {
+      name = "filter_prediction";
+      by = B * A * 4 + B * (int64_t)e->max_dets * (int64_t)sizeof(sqdet_det);
+    }
+  }
+  if (name_buf && name_cap > 0) {
+    strncpy(name_buf, name.c_str(), (size_t)name_cap - 1);
+    name_buf[name_cap - 1] = 0;
+  }
+  if (flops) *flops = fl;
+  if (params) *params = pa;
+  if (min_bytes) *min_bytes = by;
+  return SQDET_OK;
+}
+
+int sqdet_forward(sqdet_engine* e, const float* images_dev, void* stream) {
+  return forward_impl(e, images_dev, (cudaStream_t)stream);
+}
+
+int sqdet_forward_profiled(sqdet_engine* e, const float* images_dev, void* stream_v,
+                           float* op_ms) {
+  if (!e || !op_ms) return fail(SQDET_ERR_INVALID_ARG, "sqdet_forward_profiled: null argument");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_forward_profiled before sqdet_finalize");
+  if (!images_dev) return fail(SQDET_ERR_INVALID_ARG, "null images pointer");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  DeviceGuard guard(e->device);
+  int rc = prepare_params(e);
+  if (rc) return rc;
+  const int n = (int)e->ops.size() + 2;
+  while ((int)e->prof_events.size() < n + 1) {
+    cudaEvent_t ev;
+    SQ_CUDA(cudaEventCreate(&ev));
+    e->prof_events.push_back(ev);
+  }
+  SQ_CUDA(cudaEventRecord(e->prof_events[0], stream));
+  for (int i = 0; i < (int)e->ops.size(); ++i) {
+    rc = run_op(e, e->ops[i], images_dev, stream);
+    if (rc) return rc;
+    SQ_CUDA(cudaEventRecord(e->prof_events[i + 1], stream));
+  }
+  const sqdet_config& c = e->cfg;
+  rc = launch_interpret(e->tensors[e->preds].dev, e->d_anchors, e->d_boxes, e->d_probs, e->d_cls,
+                        c.batch_size, e->grid_h, e->grid_w, c.anchors_per_grid, c.classes,
+                        c.image_width, c.image_height, c.exp_thresh, stream);
+  if (rc) return rc;
+  SQ_CUDA(cudaEventRecord(e->prof_events[n - 1], stream));
+  rc = launch_topk_nms(e->d_boxes, e->d_probs, e->d_cls, c.batch_size, (int)e->num_anchors,
+                       c.classes, c.top_n_detection, c.prob_thresh, c.nms_thresh, e->d_dets,
+                       e->d_counts, e->max_dets, stream);
+  if (rc) return rc;
+  SQ_CUDA(cudaEventRecord(e->prof_events[n], stream));
+  SQ_CUDA(cudaEventSynchronize(e->prof_events[n]));
+  for (int i = 0; i < n; ++i)
+    SQ_CUDA(cudaEventElapsedTime(&op_ms[i], e->prof_events[i], e->prof_events[i + 1]));
+  return SQDET_OK;
+}
+
+int sqdet_results_dev(sqdet_engine* e, float** det_boxes, float** det_probs, int64_t** det_class,
+                      sqdet_det** dets, int32_t** counts, int32_t* max_dets) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_results_dev before sqdet_finalize");
+  if (det_boxes) *det_boxes = e->d_boxes;
+  if (det_probs) *det_probs = e->d_probs;
+  if (det_class) *det_class = e->d_cls;
+  if (dets) *dets = e->d_dets;
+  if (counts) *counts = e->d_counts;
+  if (max_dets) *max_dets = e->max_dets;
+  return SQDET_OK;
+}
+
+int sqdet_detect(sqdet_engine* e, const float* images, float* det_boxes, float* det_probs,
+                 int64_t* det_class, sqdet_det* dets, int32_t* counts, void* stream_v) {
+  if (!e || !images) return fail(SQDET_ERR_INVALID_ARG, "sqdet_detect: null argument");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_detect before sqdet_finalize");
+  DeviceGuard guard(e->device);
+  cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : e->own_stream;
+  const sqdet_config& c = e->cfg;
+  const size_t in_bytes = sizeof(float) * (size_t)e->tensors[0].numel();
+  SQ_CUDA(cudaMemcpyAsync(e->d_input, images, in_bytes, cudaMemcpyHostToDevice, stream));
+  int rc = forward_impl(e, e->d_input, stream);
+  if (rc) return rc;
+  const size_t BA = (size_t)c.batch_size * (size_t)e->num_anchors;
+  if (det_boxes)
+    SQ_CUDA(cudaMemcpyAsync(det_boxes, e->d_boxes, sizeof(float) * BA * 4, cudaMemcpyDeviceToHost, stream));
+  if (det_probs)
+    SQ_CUDA(cudaMemcpyAsync(det_probs, e->d_probs, sizeof(float) * BA, cudaMemcpyDeviceToHost, stream));
+  if (det_class)
+    SQ_CUDA(cudaMemcpyAsync(det_class, e->d_cls, sizeof(int64_t) * BA, cudaMemcpyDeviceToHost, stream));
+  if (dets)
+    SQ_CUDA(cudaMemcpyAsync(dets, e->d_dets, sizeof(sqdet_det) * (size_t)c.batch_size * e->max_dets,
+                            cudaMemcpyDeviceToHost, stream));
+  if (counts)
+    SQ_CUDA(cudaMemcpyAsync(counts, e->d_counts, sizeof(int32_t) * (size_t)c.batch_size,
+                            cudaMemcpyDeviceToHost, stream));
+  SQ_CUDA(cudaStreamSynchronize(stream));
+  return SQDET_OK;
+}
+
+int sqdet_launches_per_forward(sqdet_engine* e) {
+  if (!e) return SQDET_ERR_INVALID_ARG;
+  int n = 2;   // interpret + filter
+  for (const auto& op : e->ops) n += op.launches;
+  return n;
+}
+
+// ---- stage-isolated kernels ------------------------------------------------------------------
+int sqdet_conv2d(const float* x_dev, const float* w_hwio_dev, const float* bias_dev,
+                 const float* scale_dev, const float* shift_dev, float* y_dev, int B, int H, int W,
+                 int Cin, int Cout, int size, int stride, int padding, int relu, int y_cstride,
+                 int y_coff, int math_mode, void* stream) {
+  if (!x_dev || !w_hwio_dev || !y_dev) return fail(SQDET_ERR_INVALID_ARG, "sqdet_conv2d: null pointer");
+  if (padding != SQDET_PAD_SAME && padding != SQDET_PAD_VALID)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_conv2d: padding must be SAME(0) or VALID(1)");
+  if (math_mode == SQDET_MATH_TF32X3_TC)
+    return conv2d_tc_oneshot(x_dev, w_hwio_dev, bias_dev, scale_dev, shift_dev, y_dev, B, H, W,
+                             Cin, Cout, size, stride, padding, relu, y_cstride, y_coff,
+                             (cudaStream_t)stream);
+  if (math_mode != SQDET_MATH_FP32_SIMT)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_conv2d: unknown math_mode");
+  ConvArgs a;
+  a.x = x_dev; a.w = w_hwio_dev; a.bias = bias_dev; a.scale = scale_dev; a.shift = shift_dev;
+  a.y = y_dev; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.size = size;
+  a.stride = stride; a.padding = padding; a.relu = relu; a.y_cstride = y_cstride; a.y_coff = y_coff;
+  return launch_conv_simt(a, (cudaStream_t)stream);
+}
+
+int sqdet_maxpool_nhwc(const float* x_dev, float* y_dev, int B, int H, int W, int C, int size,
+                       int stride, int padding, void* stream) {
+  if (!x_dev || !y_dev) return fail(SQDET_ERR_INVALID_ARG, "sqdet_maxpool_nhwc: null pointer");
+  if (padding != SQDET_PAD_SAME && padding != SQDET_PAD_VALID)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_maxpool_nhwc: padding must be SAME(0) or VALID(1)");
+  return launch_maxpool(x_dev, y_dev, B, H, W, C, size, stride, padding, (cudaStream_t)stream);
+}
+
+int sqdet_interpret(const float* preds_dev, const float* anchors_f32_dev, float* det_boxes_dev,
+                    float* det_probs_dev, int64_t* det_class_dev, int B, int grid_h, int grid_w,
+                    int anchors_per_grid, int classes, int image_width, int image_height,
+                    float exp_thresh, void* stream) {
+  if (!preds_dev || !anchors_f32_dev || !det_boxes_dev || !det_probs_dev || !det_class_dev)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_interpret: null pointer");
+  return launch_interpret(preds_dev, anchors_f32_dev, det_boxes_dev, det_probs_dev, det_class_dev,
+                          B, grid_h, grid_w, anchors_per_grid, classes, image_width, image_height,
+                          exp_thresh, (cudaStream_t)stream);
+}
+
+int sqdet_topk_nms(const float* boxes_dev, const float* probs_dev, const int64_t* cls_dev, int B,
+                   int A, int classes, int top_n, float prob_thresh, float nms_thresh,
+                   sqdet_det* dets_dev, int32_t* counts_dev, int max_dets, void* stream) {
+  if (!boxes_dev || !probs_dev || !cls_dev || !dets_dev || !counts_dev)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_topk_nms: null pointer");
+  return launch_topk_nms(boxes_dev, probs_dev, cls_dev, B, A, classes, top_n, prob_thresh,
+                         nms_thresh, dets_dev, counts_dev, max_dets, (cudaStream_t)stream);
+}
+
+// ---- memory helpers ------------------------------------------------------------------------------
+int sqdet_malloc(int device, int64_t bytes, void** out_dev) {
+  if (!out_dev || bytes <= 0) return fail(SQDET_ERR_INVALID_ARG, "sqdet_malloc: bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(SQDET_ERR_CUDA, "sqdet_malloc: cannot select device");
+  SQ_CUDA(cudaMalloc(out_dev, (size_t)bytes));
+  return SQDET_OK;
+}
+int sqdet_free(int device, void* dev) {
+  DeviceGuard guard(device);
+  if (dev) SQ_CUDA(cudaFree(dev));
+  return SQDET_OK;
+}
+int sqdet_malloc_host(int64_t bytes, void** out_pinned) {
+  if (!out_pinned || bytes <= 0) return fail(SQDET_ERR_INVALID_ARG, "sqdet_malloc_host: bad argument");
+  SQ_CUDA(cudaMallocHost(out_pinned, (size_t)bytes));
+  return SQDET_OK;
+}
+int sqdet_free_host(void* pinned) {
+  if (pinned) SQ_CUDA(cudaFreeHost(pinned));
+  return SQDET_OK;
+}
+int sqdet_memcpy_h2d(void* dst_dev, const void* src, int64_t bytes, void* stream) {
+  if (!dst_dev || !src || bytes < 0) return fail(SQDET_ERR_INVALID_ARG, "sqdet_memcpy_h2d: bad argument");
+  SQ_CUDA(cudaMemcpyAsync(dst_dev, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return SQDET_OK;
+}
+int sqdet_memcpy_d2h(void* dst, const void* src_dev, int64_t bytes, void* stream) {
+  if (!dst || !src_dev || bytes < 0) return fail(SQDET_ERR_INVALID_ARG, "sqdet_memcpy_d2h: bad argument");
+  SQ_CUDA(cudaMemcpyAsync(dst, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return SQDET_OK;
+}
+int sqdet_stream_sync(int device, void* stream) {
+  DeviceGuard guard(device);
+  SQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return SQDET_OK;
+}
+
+}  // extern "C"
