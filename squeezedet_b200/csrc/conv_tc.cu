@@ -1,20 +1,702 @@
-// placeholder — replaced by the tcgen05 implementation
+// tcgen05 implicit-GEMM convolution with the 3xTF32 split (SQDET_MATH_TF32X3_TC).
+//
+// Replaces tf.nn.conv2d + bias_add [+ batch_normalization] + relu of the reference
+// (src/nn_skeleton.py:539-547, :441-449) for every stride-1 conv whose Cin is a multiple
+// of 16 (all fire squeeze/expand convs, the ConvDet head, the VGG/ResNet body), and fuses
+// a fire module's expand1x1 || expand3x3 + channel concat (src/nets/squeezeDet.py:96-106)
+// into one launch.
+//
+// GEMM view per CTA:  D[128 pixels, N] += A[128 pixels, K] * W[K, N]
+//   M tile  = an 8 x 16 patch of output pixels of one image (TMEM lane = pixel)
+//   N       = one chunk of output channels (multiple of 16, <= 256; TMEM column = channel)
+//   K       = taps x Cin, walked as (tap, 32- or 16-channel chunk)
+//   A       : TMA tiled load of the NHWC activation tensor, box {KC ch, 16 w, 8 h, 1 n} at
+//             the tap-shifted coordinate; out-of-image coordinates are zero-filled by the
+//             TMA unit = TF "SAME" zero padding; lands K-major with the 128B/64B swizzle.
+//   W       : host-packed [chunk][tap][kchunk][N][KC] fp32 (hi and lo halves), 2-D TMA.
+// Precision: fp32 operands are split a = a_hi + a_lo with a_hi = rn_tf32(a),
+//   a_lo = rn_tf32(a - a_hi); D += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation
+//   in TMEM (kind::tf32).  Dropped term a_lo*b_lo ~ 2^-22: fp32-grade results, which the
+//   1e-4 parity bar against the fp32 reference needs through ~25 stacked convs (plain TF32
+//   or BF16 miss it by 1-2 orders of magnitude).  The activation split runs in shared
+//   memory (4 warps) between the TMA landing and the MMA issue; weights are pre-split.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
+//   (one elected thread), warps 2-5 = operand splitter during the main loop, then the
+//   epilogue (tcgen05.ld -> +bias [*scale+shift] -> relu -> 128-bit global stores).
+// Pipelines: full[s] (TMA -> splitter), split[s] (splitter -> MMA), empty[s]
+//   (tcgen05.commit -> TMA), accum (tcgen05.commit -> epilogue).
+// Roofline: SqueezeDet fire2-9 are HBM-bound even fused (AI 24-95 FLOP/B fp32 I/O),
+//   fire10/11 ~ridge, ConvDet tensor-bound; 3xTF32 costs 3 MMAs at the
+//   TF32 rate per algorithmic MAC.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
 #include "common.cuh"
 #include "conv_tc.cuh"
+
 namespace sqdet {
-int tc_conv_plan(TcConvPlan* plan, int, int, int, int, int, int, int, int, int, bool, int, int,
-                 const float*, float*) { plan->enabled = false; return 0; }
-int tc_fire_plan(TcFirePlan* plan, int, int, int, int, int, int, const float*, float*) {
-  plan->enabled = false; return 0; }
-int tc_conv_pack_weights(TcConvPlan*, const float*, const float*) { return 0; }
-int tc_fire_pack_weights(TcFirePlan*, const float*, const float*, const float*, const float*) { return 0; }
-int launch_conv_tc(const TcConvPlan&, const float*, float*, cudaStream_t) {
-  return fail(SQDET_ERR_UNSUPPORTED, "tensor-core conv not built"); }
-int launch_fire_expand_tc(const TcFirePlan&, const float*, float*, cudaStream_t) {
-  return fail(SQDET_ERR_UNSUPPORTED, "tensor-core fire not built"); }
-void tc_conv_release(TcConvPlan*) {}
-void tc_fire_release(TcFirePlan*) {}
-int conv2d_tc_oneshot(const float*, const float*, const float*, const float*, const float*, float*,
-                      int, int, int, int, int, int, int, int, int, int, int, cudaStream_t) {
-  return fail(SQDET_ERR_UNSUPPORTED, "tensor-core conv not built"); }
+namespace {
+
+constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;   // 128 pixels
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_STAGES = 4;
+
+struct TcChunk {
+  int ksize;        // 1 or 3 (square)
+  int pad;          // SAME: (ksize-1)/2
+  int w_row_base;   // first row of this chunk in the packed weight matrix (hi half)
+  int ch_base;      // output channel (within this conv group) of TMEM column 0
+  int ch_count;     // valid output channels in this chunk
+  int y_coff;       // channel offset of ch_base..ch_base+ch_count in the output tensor
+  int bias_base;    // index of ch_base in the bias/scale/shift arrays
+};
+
+struct TcParams {
+  CUtensorMap tmA;
+  CUtensorMap tmW;
+  const float* bias;    // may be null
+  const float* scale;   // may be null (frozen BN)
+  const float* shift;
+  float* y;
+  int B, Ho, Wo, tiles_h, tiles_w;
+  int kch;              // Cin / KC
+  int N;                // UMMA N (uniform over chunks)
+  int tmem_cols;        // power of two >= max(32, N)
+  int y_cstride, relu;
+  int lo_row_offset;    // rows between the hi and the lo copy of the packed weights
+  int stages;
+  int nchunks;
+  TcChunk chunk[MAX_CHUNKS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, single CTA.
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand whose rows are exactly one swizzle span
+// wide (128 B for SWIZZLE_128B, 64 B for SWIZZLE_64B): 8-row groups are contiguous
+// (SBO = 8 * row bytes), LBO is unused for swizzled K-major (encoded 1), version = 1.
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  constexpr uint64_t row_bytes = KC * 4;
+  constexpr uint64_t sbo = (8 * row_bytes) >> 4;
+  constexpr uint64_t layout = (KC == 32) ? 2ull /*SWIZZLE_128B*/ : 4ull /*SWIZZLE_64B*/;
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
+         (layout << 61);
+}
+
+__device__ __forceinline__ float rn_tf32(float x) {
+  // round-to-nearest (ties away) onto the 10-bit TF32 mantissa; low 13 bits end up zero so
+  // the value is exact whatever rounding the tensor core applies to its fp32 inputs.
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                             ~uintptr_t(1023));
+  constexpr int A_BYTES = TILE_M * KC * 4;
+  const int B_BYTES = p.N * KC * 4;
+  const int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  const int S = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * STAGE_BYTES);
+  uint64_t* full = bars;                    // [S]  TMA -> splitter
+  uint64_t* split = bars + MAX_STAGES;      // [S]  splitter -> MMA
+  uint64_t* empty = bars + 2 * MAX_STAGES;  // [S]  MMA -> TMA
+  uint64_t* accum = bars + 3 * MAX_STAGES;  // [1]  MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcChunk ck = p.chunk[blockIdx.y];
+  int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w;
+  tile /= p.tiles_w;
+  const int th = tile % p.tiles_h;
+  const int img = tile / p.tiles_h;
+  const int h0 = th * TILE_H, w0 = tw * TILE_W;
+  const int taps = ck.ksize * ck.ksize;
+  const int iters = taps * p.kch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer =====================================
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (uint32_t)(it / S) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        mbar_expect_tx(&full[s], (uint32_t)(A_BYTES + 2 * B_BYTES));
+        const int tap = it / p.kch, kc = it - tap * p.kch;
+        const int dy = tap / ck.ksize, dx = tap - dy * ck.ksize;
+        tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
+        const int row = ck.w_row_base + it * p.N;
+        tma_load_2d(st + 2 * A_BYTES, &p.tmW, &full[s], 0, row);
+        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &p.tmW, &full[s], 0, row + p.lo_row_offset);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =========================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) |
+                             ((uint32_t)(TILE_M >> 4) << 24);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (uint32_t)(it / S) & 1u;
+        mbar_wait(&split[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES;
+        const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int j = 0; j < KC / 8; ++j) {
+          const uint32_t ko = j * 32;   // 8 tf32 = 32 bytes along K inside the swizzle span
+          const uint64_t dah = make_desc<KC>(a_hi + ko), dal = make_desc<KC>(a_lo + ko);
+          const uint64_t dbh = make_desc<KC>(b_hi + ko), dbl = make_desc<KC>(b_lo + ko);
+          umma_tf32(tmem_base, dal, dbh, idesc, (it | j) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(accum);            // accumulator complete
+    }
+  } else {
+    // ====================== operand splitter (main loop), then epilogue ===================
+    const int t = threadIdx.x - 64;   // 0..127
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
+      mbar_wait(&full[s], ph);
+      float4* ahi = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES);
+      float4* alo = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+      for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+        const int idx = i * 128 + t;
+        const float4 v = ahi[idx];
+        float4 h, l;
+        h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
+        l.x = rn_tf32(v.x - h.x); l.y = rn_tf32(v.y - h.y);
+        l.z = rn_tf32(v.z - h.z); l.w = rn_tf32(v.w - h.w);
+        ahi[idx] = h;
+        alo[idx] = l;
+      }
+      fence_async_proxy();           // generic-proxy stores -> visible to the tensor core
+      mbar_arrive(&split[s]);
+    }
+    // ---- epilogue ----
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                 // accumulator row = pixel within the tile
+    const int oh = h0 + (r >> 4), ow = w0 + (r & 15);
+    const bool pix_ok = (oh < p.Ho) && (ow < p.Wo);
+    float* yrow = p.y + (((size_t)img * p.Ho + oh) * p.Wo + ow) * (size_t)p.y_cstride + ck.y_coff;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.N; c0 += 16) {
+      if (c0 >= ck.ch_count) break;              // warp-uniform
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)c0, v);
+      if (pix_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int c = c0 + g * 4;
+          if (c + 3 < ck.ch_count) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float f = __uint_as_float(v[g * 4 + e]);
+              const int bi = ck.bias_base + c + e;
+              if (p.bias) f += __ldg(p.bias + bi);
+              if (p.scale) f = f * __ldg(p.scale + bi) + __ldg(p.shift + bi);
+              if (p.relu) f = fmaxf(f, 0.f);
+              o[e] = f;
+            }
+            *reinterpret_cast<float4*>(yrow + c) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (c + e < ck.ch_count) {
+                float f = __uint_as_float(v[g * 4 + e]);
+                const int bi = ck.bias_base + c + e;
+                if (p.bias) f += __ldg(p.bias + bi);
+                if (p.scale) f = f * __ldg(p.scale + bi) + __ldg(p.shift + bi);
+                if (p.relu) f = fmaxf(f, 0.f);
+                yrow[c + e] = f;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+struct ConvGroup {        // one conv reading the shared input; >= 1 chunks
+  int ksize, Cout, y_coff, bias_base;
+};
+
+struct TcImpl {
+  TcParams prm;
+  int KC = 32;
+  int Cin = 0;
+  size_t smem_bytes = 0;
+  dim3 grid;
+  float* d_w = nullptr;        // packed weights: hi rows then lo rows, [rows][KC]
+  float* d_bias = nullptr;     // concatenated per-group bias (or null)
+  float* d_scale = nullptr;
+  float* d_shift = nullptr;
+  int rows_half = 0;
+  int bias_total = 0;
+  std::vector<ConvGroup> groups;
+  std::vector<TcChunk> chunks;
+};
+
+static inline float host_rn_tf32(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+static int encode_act_map(CUtensorMap* map, const float* x, int B, int H, int W, int C, int KC) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(SQDET_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)KC, TILE_W, TILE_H, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(activation) failed: CUresult %d", (int)r);
+    return fail(SQDET_ERR_CUDA, buf);
+  }
+  return SQDET_OK;
+}
+
+static int encode_w_map(CUtensorMap* map, const float* w, int rows, int KC, int N) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(SQDET_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)KC * 4};
+  cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)N};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
+    return fail(SQDET_ERR_CUDA, buf);
+  }
+  return SQDET_OK;
+}
+
+// Common planner: `groups` convs (same ksize rules as the fire pair) over one input.
+static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vector<ConvGroup>& groups,
+                       int relu, bool has_affine, int y_cstride, const float* x_dev, float* y_dev) {
+  im->Cin = Cin;
+  im->KC = (Cin % 32 == 0) ? 32 : 16;
+  const int KC = im->KC;
+  im->groups = groups;
+  // uniform N over all chunks
+  int maxc = 0;
+  for (auto& g : groups) maxc = g.Cout > maxc ? g.Cout : maxc;
+  int N = 0;
+  {
+    const int nsplit = (maxc + 255) / 256;
+    N = ((maxc + nsplit - 1) / nsplit + 15) / 16 * 16;
+  }
+  TcParams& P = im->prm;
+  memset(&P, 0, sizeof P);
+  im->chunks.clear();
+  int row = 0;
+  const int kch = Cin / KC;
+  for (auto& g : groups) {
+    for (int cb = 0; cb < g.Cout; cb += N) {
+      TcChunk c;
+      c.ksize = g.ksize;
+      c.pad = (g.ksize - 1) / 2;
+      c.w_row_base = row;
+      c.ch_base = cb;
+      c.ch_count = (g.Cout - cb) < N ? (g.Cout - cb) : N;
+      c.y_coff = g.y_coff + cb;
+      c.bias_base = g.bias_base + cb;
+      row += g.ksize * g.ksize * kch * N;
+      im->chunks.push_back(c);
+    }
+  }
+  if ((int)im->chunks.size() > MAX_CHUNKS) return 0;   // not taken by this path
+  im->rows_half = row;
+  im->bias_total = 0;
+  for (auto& g : groups) im->bias_total = (g.bias_base + g.Cout) > im->bias_total ? (g.bias_base + g.Cout) : im->bias_total;
+  P.B = B; P.Ho = H; P.Wo = W;                      // stride-1 SAME: output grid == input grid
+  P.tiles_h = (H + TILE_H - 1) / TILE_H;
+  P.tiles_w = (W + TILE_W - 1) / TILE_W;
+  P.kch = kch;
+  P.N = N;
+  int cols = 32;
+  while (cols < N) cols <<= 1;
+  P.tmem_cols = cols;
+  P.y_cstride = y_cstride;
+  P.relu = relu;
+  P.lo_row_offset = row;
+  P.nchunks = (int)im->chunks.size();
+  for (int i = 0; i < P.nchunks; ++i) P.chunk[i] = im->chunks[i];
+  const size_t stage = (size_t)2 * TILE_M * KC * 4 + (size_t)2 * N * KC * 4;
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return 0;
+  P.stages = stages;
+  im->smem_bytes = stages * stage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  im->grid = dim3((unsigned)(B * P.tiles_h * P.tiles_w), (unsigned)P.nchunks);
+  P.y = y_dev;
+  SQ_CUDA(cudaMalloc(&im->d_w, sizeof(float) * (size_t)row * 2 * KC));
+  SQ_CUDA(cudaMemset(im->d_w, 0, sizeof(float) * (size_t)row * 2 * KC));
+  SQ_CUDA(cudaMalloc(&im->d_bias, sizeof(float) * im->bias_total));
+  SQ_CUDA(cudaMemset(im->d_bias, 0, sizeof(float) * im->bias_total));
+  P.bias = im->d_bias;
+  if (has_affine) {
+    SQ_CUDA(cudaMalloc(&im->d_scale, sizeof(float) * im->bias_total));
+    SQ_CUDA(cudaMalloc(&im->d_shift, sizeof(float) * im->bias_total));
+    P.scale = im->d_scale;
+    P.shift = im->d_shift;
+  }
+  int rc = encode_act_map(&P.tmA, x_dev, B, H, W, Cin, KC);
+  if (rc) return rc;
+  rc = encode_w_map(&P.tmW, im->d_w, row * 2, KC, N);
+  if (rc) return rc;
+  // opt in to the full 227 KB once for both instantiations (the attribute is per function,
+  // not per launch, so it must cover the largest plan)
+  static bool attr_set = false;
+  if (!attr_set) {
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 232448));
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 232448));
+    attr_set = true;
+  }
+  return 1;
+}
+
+// Pack group `gi` weights (HWIO [k,k,Cin,Cout]) into the [chunk][tap][kchunk][N][KC] hi/lo rows.
+static void pack_group(const TcImpl* im, int gi, const float* w_hwio, std::vector<float>& packed) {
+  const int KC = im->KC, N = im->prm.N, kch = im->prm.kch, Cin = im->Cin;
+  const ConvGroup& g = im->groups[gi];
+  const size_t lo_off = (size_t)im->rows_half * KC;
+  // chunks of this group appear in order; find the first
+  int ci = 0;
+  for (int i = 0; i < gi; ++i) ci += (im->groups[i].Cout + N - 1) / N;
+  for (int cb = 0; cb < g.Cout; cb += N, ++ci) {
+    const TcChunk& c = im->chunks[ci];
+    for (int tap = 0; tap < g.ksize * g.ksize; ++tap)
+      for (int kc = 0; kc < kch; ++kc)
+        for (int n = 0; n < c.ch_count; ++n) {
+          const size_t rowi = (size_t)c.w_row_base + ((size_t)tap * kch + kc) * N + n;
+          for (int k = 0; k < KC; ++k) {
+            const float v = w_hwio[((size_t)tap * Cin + (size_t)kc * KC + k) * g.Cout + cb + n];
+            const float hi = host_rn_tf32(v);
+            packed[rowi * KC + k] = hi;
+            packed[lo_off + rowi * KC + k] = host_rn_tf32(v - hi);
+          }
+        }
+  }
+}
+
+static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaStream_t stream) {
+  // the tensor map bakes in the activation address the plan was made for
+  (void)x_dev;
+  (void)y_dev;
+  if (im->KC == 32)
+    conv_tc_kernel<32><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(im->prm);
+  else
+    conv_tc_kernel<16><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(im->prm);
+  SQ_CHECK_LAUNCH("conv_tc_kernel");
+  return SQDET_OK;
+}
+
+static void release_impl(void** impl) {
+  if (!*impl) return;
+  TcImpl* im = static_cast<TcImpl*>(*impl);
+  cudaFree(im->d_w);
+  cudaFree(im->d_bias);
+  cudaFree(im->d_scale);
+  cudaFree(im->d_shift);
+  delete im;
+  *impl = nullptr;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+int tc_conv_plan(TcConvPlan* plan, int B, int H, int W, int Cin, int Cout, int size, int stride,
+                 int padding, int relu, bool has_affine, int y_cstride, int y_coff,
+                 const float* x_dev, float* y_dev) {
+  plan->enabled = false;
+  // shapes this path takes: stride-1 SAME, 1x1 or 3x3, Cin a multiple of 16, 16B-aligned stores
+  if (stride != 1 || padding != SQDET_PAD_SAME || (size != 1 && size != 3)) return 0;
+  if (Cin % 16 != 0 || Cin < 16 || (y_cstride % 4) || (y_coff % 4) || (Cout % 4)) return 0;
+  TcImpl* im = new TcImpl();
+  std::vector<ConvGroup> groups = {{size, Cout, y_coff, 0}};
+  int rc = plan_common(im, B, H, W, Cin, groups, relu, has_affine, y_cstride, x_dev, y_dev);
+  if (rc <= 0) {
+    void* p = im;
+    release_impl(&p);
+    return rc;
+  }
+  plan->enabled = true;
+  plan->B = B; plan->H = H; plan->W = W; plan->Cin = Cin; plan->Cout = Cout;
+  plan->size = size; plan->stride = stride; plan->relu = relu; plan->Ho = H; plan->Wo = W;
+  plan->y_cstride = y_cstride; plan->y_coff = y_coff;
+  plan->impl = im;
+  return 1;
+}
+
+int tc_fire_plan(TcFirePlan* plan, int B, int H, int W, int S, int E1, int E3, const float* q_dev,
+                 float* y_dev) {
+  plan->enabled = false;
+  if (S % 16 != 0 || S < 16 || (E1 % 4) || (E3 % 4)) return 0;
+  TcImpl* im = new TcImpl();
+  std::vector<ConvGroup> groups = {{1, E1, 0, 0}, {3, E3, E1, E1}};
+  int rc = plan_common(im, B, H, W, S, groups, 1, false, E1 + E3, q_dev, y_dev);
+  if (rc <= 0) {
+    void* p = im;
+    release_impl(&p);
+    return rc;
+  }
+  plan->enabled = true;
+  plan->B = B; plan->H = H; plan->W = W; plan->S = S; plan->E1 = E1; plan->E3 = E3;
+  plan->impl = im;
+  return 1;
+}
+
+int tc_conv_pack_weights(TcConvPlan* plan, const float* w_hwio, const float* bias) {
+  TcImpl* im = static_cast<TcImpl*>(plan->impl);
+  std::vector<float> packed((size_t)im->rows_half * 2 * im->KC, 0.f);
+  pack_group(im, 0, w_hwio, packed);
+  SQ_CUDA(cudaMemcpy(im->d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (bias)
+    SQ_CUDA(cudaMemcpy(im->d_bias, bias, sizeof(float) * plan->Cout, cudaMemcpyHostToDevice));
+  return SQDET_OK;
+}
+
+int tc_conv_set_affine(TcConvPlan* plan, const float* scale, const float* shift) {
+  TcImpl* im = static_cast<TcImpl*>(plan->impl);
+  if (!im->d_scale) return fail(SQDET_ERR_STATE, "tc conv planned without an affine epilogue");
+  SQ_CUDA(cudaMemcpy(im->d_scale, scale, sizeof(float) * plan->Cout, cudaMemcpyHostToDevice));
+  SQ_CUDA(cudaMemcpy(im->d_shift, shift, sizeof(float) * plan->Cout, cudaMemcpyHostToDevice));
+  return SQDET_OK;
+}
+
+int tc_fire_pack_weights(TcFirePlan* plan, const float* w_e1, const float* b_e1, const float* w_e3,
+                         const float* b_e3) {
+  TcImpl* im = static_cast<TcImpl*>(plan->impl);
+  std::vector<float> packed((size_t)im->rows_half * 2 * im->KC, 0.f);
+  pack_group(im, 0, w_e1, packed);
+  pack_group(im, 1, w_e3, packed);
+  SQ_CUDA(cudaMemcpy(im->d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  SQ_CUDA(cudaMemcpy(im->d_bias, b_e1, sizeof(float) * plan->E1, cudaMemcpyHostToDevice));
+  SQ_CUDA(cudaMemcpy(im->d_bias + plan->E1, b_e3, sizeof(float) * plan->E3, cudaMemcpyHostToDevice));
+  return SQDET_OK;
+}
+
+int launch_conv_tc(const TcConvPlan& plan, const float* x_dev, float* y_dev, cudaStream_t stream) {
+  return launch_impl(static_cast<const TcImpl*>(plan.impl), x_dev, y_dev, stream);
+}
+
+int launch_fire_expand_tc(const TcFirePlan& plan, const float* q_dev, float* y_dev,
+                          cudaStream_t stream) {
+  return launch_impl(static_cast<const TcImpl*>(plan.impl), q_dev, y_dev, stream);
+}
+
+void tc_conv_release(TcConvPlan* plan) {
+  release_impl(&plan->impl);
+  plan->enabled = false;
+}
+void tc_fire_release(TcFirePlan* plan) {
+  release_impl(&plan->impl);
+  plan->enabled = false;
+}
+
+int conv2d_tc_oneshot(const float* x_dev, const float* w_hwio_dev, const float* bias_dev,
+                      const float* scale_dev, const float* shift_dev, float* y_dev, int B, int H,
+                      int W, int Cin, int Cout, int size, int stride, int padding, int relu,
+                      int y_cstride, int y_coff, cudaStream_t stream) {
+  TcConvPlan plan;
+  int rc = tc_conv_plan(&plan, B, H, W, Cin, Cout, size, stride, padding, relu,
+                        scale_dev != nullptr, y_cstride, y_coff, x_dev, y_dev);
+  if (rc < 0) return rc;
+  if (rc == 0) {
+    // shape not taken by the tensor-core path (e.g. conv1, Cin = 3): same dispatch as the engine
+    ConvArgs a;
+    a.x = x_dev; a.w = w_hwio_dev; a.bias = bias_dev; a.scale = scale_dev; a.shift = shift_dev;
+    a.y = y_dev; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.size = size;
+    a.stride = stride; a.padding = padding; a.relu = relu; a.y_cstride = y_cstride; a.y_coff = y_coff;
+    return launch_conv_simt(a, stream);
+  }
+  std::vector<float> w((size_t)size * size * Cin * Cout), b(Cout, 0.f), sc, sh;
+  SQ_CUDA(cudaMemcpy(w.data(), w_hwio_dev, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  if (bias_dev) SQ_CUDA(cudaMemcpy(b.data(), bias_dev, Cout * sizeof(float), cudaMemcpyDeviceToHost));
+  rc = tc_conv_pack_weights(&plan, w.data(), bias_dev ? b.data() : nullptr);
+  if (!rc && scale_dev) {
+    sc.resize(Cout); sh.resize(Cout);
+    SQ_CUDA(cudaMemcpy(sc.data(), scale_dev, Cout * sizeof(float), cudaMemcpyDeviceToHost));
+    SQ_CUDA(cudaMemcpy(sh.data(), shift_dev, Cout * sizeof(float), cudaMemcpyDeviceToHost));
+    rc = tc_conv_set_affine(&plan, sc.data(), sh.data());
+  }
+  if (!rc) rc = launch_conv_tc(plan, x_dev, y_dev, stream);
+  cudaError_t ce = cudaStreamSynchronize(stream);
+  tc_conv_release(&plan);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return cuda_fail(ce, "conv2d_tc_oneshot sync");
+  return SQDET_OK;
+}
+
+}  // namespace sqdet

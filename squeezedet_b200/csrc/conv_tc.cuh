@@ -30,6 +30,7 @@ int tc_conv_plan(TcConvPlan* plan, int B, int H, int W, int Cin, int Cout, int s
 int tc_fire_plan(TcFirePlan* plan, int B, int H, int W, int S, int E1, int E3,
                  const float* q_dev, float* y_dev);
 int tc_conv_pack_weights(TcConvPlan* plan, const float* w_hwio, const float* bias);
+int tc_conv_set_affine(TcConvPlan* plan, const float* scale, const float* shift);
 int tc_fire_pack_weights(TcFirePlan* plan, const float* w_e1, const float* b_e1,
                          const float* w_e3, const float* b_e3);
 int launch_conv_tc(const TcConvPlan& plan, const float* x_dev, float* y_dev, cudaStream_t stream);

@@ -287,6 +287,10 @@ static int prepare_params(sqdet_engine* e) {
         if (!c.shift) SQ_CUDA(cudaMalloc(&c.shift, sizeof(float) * n));
         SQ_CUDA(cudaMemcpy(c.scale, sc.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
         SQ_CUDA(cudaMemcpy(c.shift, sh.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+        if (c.tc.enabled) {
+          int rc = tc_conv_set_affine(&c.tc, sc.data(), sh.data());
+          if (rc) return rc;
+        }
       }
     }
   }
@@ -426,10 +430,10 @@ int sqdet_destroy(sqdet_engine* e) {
   cudaFree(e->d_boxes);
   cudaFree(e->d_probs);
   cudaFree(e->d_cls);
-  cudaFree(e->d_dets);   // also owns d_counts (one blob)
-  cudaFree(e->d_input);
+  cudaFree(e->d_dets);   // also owns d_counts (one blob); d_input aliases tensors[0].dev
   for (auto ev : e->prof_events) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  (void)cudaGetLastError();   // never leave a stale error for the next engine's launch checks
   delete e;
   return SQDET_OK;
 }
