@@ -20,11 +20,18 @@
 //   1e-4 parity bar against the fp32 reference needs through ~25 stacked convs (plain TF32
 //   or BF16 miss it by 1-2 orders of magnitude).  The activation split runs in shared
 //   memory (4 warps) between the TMA landing and the MMA issue; weights are pre-split.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
-//   (one elected thread), warps 2-5 = operand splitter during the main loop, then the
-//   epilogue (tcgen05.ld -> +bias [*scale+shift] -> relu -> 128-bit global stores).
+// Accumulation: the tensor core adds into its fp32 accumulator with truncation (measured
+//   on B200: error grows linearly with the number of chained MMAs, 3.6e-5 of max at K=6912
+//   vs 2e-6 for fp32 FFMA).  So a tile's K loop is cut into SEGMENTS of ~24 MMAs, each
+//   accumulated from zero in one of two TMEM buffers; the drain warps add finished segments
+//   into fp32 registers (round-to-nearest).  Bias falls by sqrt(segment/total) (~15x at the
+//   ConvDet head) and the drain of segment g overlaps the MMAs of segment g+1.
+// Persistent CTAs (one per SM, 320 threads), static round-robin over (chunk, tile) items:
+//   warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected thread),
+//   warps 2-5 = operand splitter, warps 6-9 = segment drain + epilogue
+//   (tcgen05.ld -> fp32 add -> +bias [*scale+shift] -> relu -> 128-bit global stores).
 // Pipelines: full[s] (TMA -> splitter), split[s] (splitter -> MMA), empty[s]
-//   (tcgen05.commit -> TMA), accum (tcgen05.commit -> epilogue).
+//   (tcgen05.commit -> TMA), tfull[b] (tcgen05.commit -> drain), tempty[b] (drain -> MMA).
 // Roofline: SqueezeDet fire2-9 are HBM-bound even fused (AI 24-95 FLOP/B fp32 I/O),
 //   fire10/11 ~ridge, ConvDet tensor-bound; 3xTF32 costs 3 MMAs at the
 //   TF32 rate per algorithmic MAC.
@@ -43,8 +50,9 @@ namespace sqdet {
 namespace {
 
 constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;   // 128 pixels
-constexpr int NUM_THREADS = 192;
-constexpr int MAX_CHUNKS = 8;
+constexpr int NUM_THREADS = 320;
+constexpr int MAX_CHUNKS = 16;
+constexpr int MAX_N = 128;          // output channels per item (register-resident running sums)
 constexpr int MAX_STAGES = 4;
 
 struct TcChunk {
@@ -67,7 +75,9 @@ struct TcParams {
   int B, Ho, Wo, tiles_h, tiles_w;
   int kch;              // Cin / KC
   int N;                // UMMA N (uniform over chunks)
-  int tmem_cols;        // power of two >= max(32, N)
+  int tmem_cols;        // power of two >= max(32, 2*N): two accumulator buffers
+  int seg_stages;       // pipeline stages (K blocks) per accumulation segment
+  int ntiles;           // B * tiles_h * tiles_w
   int y_cstride, relu;
   int lo_row_offset;    // rows between the hi and the lo copy of the packed weights
   int stages;
@@ -157,7 +167,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+// 16 accumulator columns of this warp's 32 lanes, without waiting (pair with tmem_wait_ld).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -166,6 +177,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
@@ -202,19 +215,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   uint64_t* full = bars;                    // [S]  TMA -> splitter
   uint64_t* split = bars + MAX_STAGES;      // [S]  splitter -> MMA
   uint64_t* empty = bars + 2 * MAX_STAGES;  // [S]  MMA -> TMA
-  uint64_t* accum = bars + 3 * MAX_STAGES;  // [1]  MMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 1);
+  uint64_t* tfull = bars + 3 * MAX_STAGES;  // [2]  MMA -> drain (segment accumulated)
+  uint64_t* tempty = tfull + 2;             // [2]  drain -> MMA (buffer read out)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TcChunk ck = p.chunk[blockIdx.y];
-  int tile = blockIdx.x;
-  const int tw = tile % p.tiles_w;
-  tile /= p.tiles_w;
-  const int th = tile % p.tiles_h;
-  const int img = tile / p.tiles_h;
-  const int h0 = th * TILE_H, w0 = tw * TILE_W;
-  const int taps = ck.ksize * ck.ksize;
-  const int iters = taps * p.kch;
+  const int total_items = p.ntiles * p.nchunks;
+  const int G = p.seg_stages;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -222,7 +229,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       mbar_init(&split[s], 128);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -231,21 +241,32 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Items are ordered chunk-major (all tiles of chunk 0, then chunk 1, ...) so that the static
+  // round-robin gives every CTA the same mix of cheap (1x1) and expensive (3x3) items.
   if (warp == 0) {
     // ================================ TMA producer =====================================
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (uint32_t)(it / S) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-        mbar_expect_tx(&full[s], (uint32_t)(A_BYTES + 2 * B_BYTES));
-        const int tap = it / p.kch, kc = it - tap * p.kch;
-        const int dy = tap / ck.ksize, dx = tap - dy * ck.ksize;
-        tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
-        const int row = ck.w_row_base + it * p.N;
-        tma_load_2d(st + 2 * A_BYTES, &p.tmW, &full[s], 0, row);
-        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &p.tmW, &full[s], 0, row + p.lo_row_offset);
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const TcChunk ck = p.chunk[item / p.ntiles];
+        int tile = item % p.ntiles;
+        const int tw = tile % p.tiles_w;
+        tile /= p.tiles_w;
+        const int h0 = (tile % p.tiles_h) * TILE_H, w0 = tw * TILE_W, img = tile / p.tiles_h;
+        const int iters = ck.ksize * ck.ksize * p.kch;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+          mbar_expect_tx(&full[s], (uint32_t)(A_BYTES + 2 * B_BYTES));
+          const int tap = i / p.kch, kc = i - tap * p.kch;
+          const int dy = tap / ck.ksize, dx = tap - dy * ck.ksize;
+          tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
+          const int row = ck.w_row_base + i * p.N;
+          tma_load_2d(st + 2 * A_BYTES, &p.tmW, &full[s], 0, row);
+          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &p.tmW, &full[s], 0, row + p.lo_row_offset);
+        }
       }
     }
   } else if (warp == 1) {
@@ -253,91 +274,134 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) |
                              ((uint32_t)(TILE_M >> 4) << 24);
-      for (int it = 0; it < iters; ++it) {
+      int it = 0, g = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const TcChunk ck = p.chunk[item / p.ntiles];
+        const int iters = ck.ksize * ck.ksize * p.kch;
+        for (int i0 = 0; i0 < iters; i0 += G, ++g) {
+          const int buf = g & 1;
+          mbar_wait(&tempty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);   // buffer drained
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
+          const int i1 = (i0 + G < iters) ? (i0 + G) : iters;
+          for (int i = i0; i < i1; ++i, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(&split[s], ph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES);
+            const uint32_t a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_BYTES;
+            const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+            for (int j = 0; j < KC / 8; ++j) {
+              const uint32_t ko = j * 32;   // 8 tf32 = 32 bytes along K inside the swizzle span
+              const uint64_t dah = make_desc<KC>(a_hi + ko), dal = make_desc<KC>(a_lo + ko);
+              const uint64_t dbh = make_desc<KC>(b_hi + ko), dbl = make_desc<KC>(b_lo + ko);
+              umma_tf32(d_tmem, dal, dbh, idesc, (i != i0 || j != 0) ? 1u : 0u);
+              umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+              umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+            }
+            umma_commit(&empty[s]);    // frees the smem stage once these MMAs have read it
+          }
+          umma_commit(&tfull[buf]);    // segment complete -> drain warps
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ================================ operand splitter ====================================
+    const int t = threadIdx.x - 64;   // 0..127
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const TcChunk ck = p.chunk[item / p.ntiles];
+      const int iters = ck.ksize * ck.ksize * p.kch;
+      for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
-        mbar_wait(&split[s], ph);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES;
-        const uint32_t b_lo = b_hi + B_BYTES;
+        mbar_wait(&full[s], ph);
+        float4* ahi = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES);
+        float4* alo = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES + A_BYTES);
 #pragma unroll
-        for (int j = 0; j < KC / 8; ++j) {
-          const uint32_t ko = j * 32;   // 8 tf32 = 32 bytes along K inside the swizzle span
-          const uint64_t dah = make_desc<KC>(a_hi + ko), dal = make_desc<KC>(a_lo + ko);
-          const uint64_t dbh = make_desc<KC>(b_hi + ko), dbl = make_desc<KC>(b_lo + ko);
-          umma_tf32(tmem_base, dal, dbh, idesc, (it | j) != 0 ? 1u : 0u);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        for (int k = 0; k < A_BYTES / 16 / 128; ++k) {
+          const int idx = k * 128 + t;
+          const float4 v = ahi[idx];
+          float4 h, l;
+          h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
+          l.x = rn_tf32(v.x - h.x); l.y = rn_tf32(v.y - h.y);
+          l.z = rn_tf32(v.z - h.z); l.w = rn_tf32(v.w - h.w);
+          ahi[idx] = h;
+          alo[idx] = l;
         }
-        umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
+        fence_async_proxy();           // generic-proxy stores -> visible to the tensor core
+        mbar_arrive(&split[s]);
       }
-      umma_commit(accum);            // accumulator complete
     }
   } else {
-    // ====================== operand splitter (main loop), then epilogue ===================
-    const int t = threadIdx.x - 64;   // 0..127
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % S;
-      const uint32_t ph = (uint32_t)(it / S) & 1u;
-      mbar_wait(&full[s], ph);
-      float4* ahi = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES);
-      float4* alo = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES + A_BYTES);
-#pragma unroll
-      for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-        const int idx = i * 128 + t;
-        const float4 v = ahi[idx];
-        float4 h, l;
-        h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
-        l.x = rn_tf32(v.x - h.x); l.y = rn_tf32(v.y - h.y);
-        l.z = rn_tf32(v.z - h.z); l.w = rn_tf32(v.w - h.w);
-        ahi[idx] = h;
-        alo[idx] = l;
-      }
-      fence_async_proxy();           // generic-proxy stores -> visible to the tensor core
-      mbar_arrive(&split[s]);
-    }
-    // ---- epilogue ----
-    mbar_wait(accum, 0);
-    tc_fence_after();
+    // ============================ segment drain + epilogue ================================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                 // accumulator row = pixel within the tile
-    const int oh = h0 + (r >> 4), ow = w0 + (r & 15);
-    const bool pix_ok = (oh < p.Ho) && (ow < p.Wo);
-    float* yrow = p.y + (((size_t)img * p.Ho + oh) * p.Wo + ow) * (size_t)p.y_cstride + ck.y_coff;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.N; c0 += 16) {
-      if (c0 >= ck.ch_count) break;              // warp-uniform
-      uint32_t v[16];
-      tmem_ld16(trow + (uint32_t)c0, v);
-      if (pix_ok) {
+    float acc[MAX_N];
+    int g = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const TcChunk ck = p.chunk[item / p.ntiles];
+      int tile = item % p.ntiles;
+      const int tw = tile % p.tiles_w;
+      tile /= p.tiles_w;
+      const int h0 = (tile % p.tiles_h) * TILE_H, w0 = tw * TILE_W, img = tile / p.tiles_h;
+      const int iters = ck.ksize * ck.ksize * p.kch;
+      const int ncols = (ck.ch_count + 15) & ~15;
+      for (int i0 = 0; i0 < iters; i0 += G, ++g) {
+        const int buf = g & 1;
+        mbar_wait(&tfull[buf], ((uint32_t)g >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.N);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int c = c0 + g * 4;
-          if (c + 3 < ck.ch_count) {
+        for (int c0 = 0; c0 < MAX_N; c0 += 32) {
+          if (c0 < ncols) {                      // warp-uniform
+            uint32_t v0[16], v1[16];
+            tmem_ld16_nowait(trow + (uint32_t)c0, v0);
+            const bool second = (c0 + 16 < ncols);
+            if (second) tmem_ld16_nowait(trow + (uint32_t)(c0 + 16), v1);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              acc[c0 + e] = (i0 == 0 ? 0.f : acc[c0 + e]) + __uint_as_float(v0[e]);
+            if (second) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                acc[c0 + 16 + e] = (i0 == 0 ? 0.f : acc[c0 + 16 + e]) + __uint_as_float(v1[e]);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[buf]);               // buffer may be overwritten by segment g+2
+      }
+      // ---- epilogue: bias [, affine], relu, 128-bit stores of this pixel's channel run ----
+      const int oh = h0 + (r >> 4), ow = w0 + (r & 15);
+      if (oh < p.Ho && ow < p.Wo) {
+        float* yrow =
+            p.y + (((size_t)img * p.Ho + oh) * p.Wo + ow) * (size_t)p.y_cstride + ck.y_coff;
+#pragma unroll
+        for (int c = 0; c < MAX_N; c += 4) {
+          if (c < ck.ch_count) {
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float f = __uint_as_float(v[g * 4 + e]);
+              float f = acc[c + e];
               const int bi = ck.bias_base + c + e;
-              if (p.bias) f += __ldg(p.bias + bi);
-              if (p.scale) f = f * __ldg(p.scale + bi) + __ldg(p.shift + bi);
+              if (c + e < ck.ch_count) {
+                if (p.bias) f += __ldg(p.bias + bi);
+                if (p.scale) f = f * __ldg(p.scale + bi) + __ldg(p.shift + bi);
+              }
               if (p.relu) f = fmaxf(f, 0.f);
               o[e] = f;
             }
-            *reinterpret_cast<float4*>(yrow + c) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
+            if (c + 3 < ck.ch_count) {
+              *reinterpret_cast<float4*>(yrow + c) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (c + e < ck.ch_count) {
-                float f = __uint_as_float(v[g * 4 + e]);
-                const int bi = ck.bias_base + c + e;
-                if (p.bias) f += __ldg(p.bias + bi);
-                if (p.scale) f = f * __ldg(p.scale + bi) + __ldg(p.shift + bi);
-                if (p.relu) f = fmaxf(f, 0.f);
-                yrow[c + e] = f;
-              }
+              for (int e = 0; e < 4; ++e)
+                if (c + e < ck.ch_count) yrow[c + e] = o[e];
             }
           }
         }
@@ -451,7 +515,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   for (auto& g : groups) maxc = g.Cout > maxc ? g.Cout : maxc;
   int N = 0;
   {
-    const int nsplit = (maxc + 255) / 256;
+    const int nsplit = (maxc + MAX_N - 1) / MAX_N;
     N = ((maxc + nsplit - 1) / nsplit + 15) / 16 * 16;
   }
   TcParams& P = im->prm;
@@ -483,8 +547,11 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   P.kch = kch;
   P.N = N;
   int cols = 32;
-  while (cols < N) cols <<= 1;
+  while (cols < 2 * N) cols <<= 1;
   P.tmem_cols = cols;
+  // ~24 chained MMAs per accumulation segment (3 MMAs per 8-wide K step)
+  P.seg_stages = (KC == 32) ? 2 : 4;
+  P.ntiles = B * P.tiles_h * P.tiles_w;
   P.y_cstride = y_cstride;
   P.relu = relu;
   P.lo_row_offset = row;
@@ -495,8 +562,14 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return 0;
   P.stages = stages;
-  im->smem_bytes = stages * stage + 1024 /*alignment slack*/ + 256 /*barriers*/;
-  im->grid = dim3((unsigned)(B * P.tiles_h * P.tiles_w), (unsigned)P.nchunks);
+  im->smem_bytes = stages * stage + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/;
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long items = (long long)P.ntiles * P.nchunks;
+    im->grid = dim3((unsigned)(items < sms ? items : sms));
+  }
   P.y = y_dev;
   SQ_CUDA(cudaMalloc(&im->d_w, sizeof(float) * (size_t)row * 2 * KC));
   SQ_CUDA(cudaMemset(im->d_w, 0, sizeof(float) * (size_t)row * 2 * KC));

