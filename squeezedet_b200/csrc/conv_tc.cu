@@ -38,7 +38,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <math_constants.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -53,7 +55,7 @@ constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;   // 128 pixels
 constexpr int NUM_THREADS = 320;
 constexpr int MAX_CHUNKS = 16;
 constexpr int MAX_N = 128;          // output channels per item (register-resident running sums)
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 12;
 
 struct TcChunk {
   int ksize;        // 1 or 3 (square)
@@ -78,6 +80,7 @@ struct TcParams {
   int tmem_cols;        // power of two >= max(32, 2*N): two accumulator buffers
   int seg_stages;       // pipeline stages (K blocks) per accumulation segment
   int ntiles;           // B * tiles_h * tiles_w
+  long long* dbg;       // optional per-CTA cycle counters (SQDET_TC_DEBUG=1), else null
   int y_cstride, relu;
   int lo_row_offset;    // rows between the hi and the lo copy of the packed weights
   int stages;
@@ -194,6 +197,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
          (layout << 61);
 }
 
+// Debug-only stall accounting: cycles spent inside a barrier wait, per role.
+#define SQ_TIMED_WAIT(counter, bar, parity)                 \
+  do {                                                      \
+    if (p.dbg) {                                            \
+      const long long _t0 = clock64();                      \
+      mbar_wait(bar, parity);                               \
+      counter += clock64() - _t0;                           \
+    } else {                                                \
+      mbar_wait(bar, parity);                               \
+    }                                                       \
+  } while (0)
+
 __device__ __forceinline__ float rn_tf32(float x) {
   // round-to-nearest (ties away) onto the 10-bit TF32 mantissa; low 13 bits end up zero so
   // the value is exact whatever rounding the tensor core applies to its fp32 inputs.
@@ -218,6 +233,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   uint64_t* tfull = bars + 3 * MAX_STAGES;  // [2]  MMA -> drain (segment accumulated)
   uint64_t* tempty = tfull + 2;             // [2]  drain -> MMA (buffer read out)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  // per-item epilogue parameters (bias, scale, shift), double-buffered by item parity
+  float* s_par = reinterpret_cast<float*>(tempty + 4);   // [2][3][MAX_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_items = p.ntiles * p.nchunks;
@@ -247,6 +264,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     // ================================ TMA producer =====================================
     if (lane == 0) {
       int it = 0;
+      long long w_empty = 0;
+      const long long t_begin = clock64();
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const TcChunk ck = p.chunk[item / p.ntiles];
         int tile = item % p.ntiles;
@@ -257,7 +276,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         for (int i = 0; i < iters; ++i, ++it) {
           const int s = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
+          SQ_TIMED_WAIT(w_empty, &empty[s], ph ^ 1u);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
           mbar_expect_tx(&full[s], (uint32_t)(A_BYTES + 2 * B_BYTES));
           const int tap = i / p.kch, kc = i - tap * p.kch;
@@ -268,57 +287,80 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           tma_load_2d(st + 2 * A_BYTES + B_BYTES, &p.tmW, &full[s], 0, row + p.lo_row_offset);
         }
       }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = w_empty;
+        p.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;
+        p.dbg[blockIdx.x * 8 + 6] = it;
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer =========================================
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform addresses/descriptors live in uniform
+    // registers); only lane 0 issues tcgen05.mma / tcgen05.commit.
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) |
                              ((uint32_t)(TILE_M >> 4) << 24);
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
+      const uint64_t desc_hi = make_desc<KC>(0) & 0xFFFFFFFF00000000ull;   // layout/SBO/version
+      const uint32_t desc_lo0 = (uint32_t)(make_desc<KC>(0) & 0xFFFFFFFFull);  // LBO field
       int it = 0, g = 0;
+      long long w_split = 0, w_tempty = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const TcChunk ck = p.chunk[item / p.ntiles];
         const int iters = ck.ksize * ck.ksize * p.kch;
         for (int i0 = 0; i0 < iters; i0 += G, ++g) {
           const int buf = g & 1;
-          mbar_wait(&tempty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);   // buffer drained
+          SQ_TIMED_WAIT(w_tempty, &tempty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);   // buffer drained
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
+          const uint32_t d_tmem = tmem_u + (uint32_t)(buf * p.N);
           const int i1 = (i0 + G < iters) ? (i0 + G) : iters;
           for (int i = i0; i < i1; ++i, ++it) {
             const int s = it % S;
             const uint32_t ph = (uint32_t)(it / S) & 1u;
-            mbar_wait(&split[s], ph);
+            SQ_TIMED_WAIT(w_split, &split[s], ph);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES);
-            const uint32_t a_lo = a_hi + A_BYTES;
-            const uint32_t b_hi = a_hi + 2 * A_BYTES;
-            const uint32_t b_lo = b_hi + B_BYTES;
+            // descriptor low words (start address >> 4 | LBO); +2 per 32-byte K step
+            const uint32_t a_hi = desc_lo0 | ((smem_base + (uint32_t)(s * STAGE_BYTES)) >> 4);
+            const uint32_t a_lo = a_hi + (A_BYTES >> 4);
+            const uint32_t b_hi = a_hi + (2 * A_BYTES >> 4);
+            const uint32_t b_lo = b_hi + (uint32_t)(B_BYTES >> 4);
+            if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < KC / 8; ++j) {
-              const uint32_t ko = j * 32;   // 8 tf32 = 32 bytes along K inside the swizzle span
-              const uint64_t dah = make_desc<KC>(a_hi + ko), dal = make_desc<KC>(a_lo + ko);
-              const uint64_t dbh = make_desc<KC>(b_hi + ko), dbl = make_desc<KC>(b_lo + ko);
-              umma_tf32(d_tmem, dal, dbh, idesc, (i != i0 || j != 0) ? 1u : 0u);
-              umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-              umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+              for (int j = 0; j < KC / 8; ++j) {
+                const uint64_t dah = desc_hi | (uint64_t)(a_hi + 2 * j);
+                const uint64_t dal = desc_hi | (uint64_t)(a_lo + 2 * j);
+                const uint64_t dbh = desc_hi | (uint64_t)(b_hi + 2 * j);
+                const uint64_t dbl = desc_hi | (uint64_t)(b_lo + 2 * j);
+                umma_tf32(d_tmem, dal, dbh, idesc, (i != i0 || j != 0) ? 1u : 0u);
+                umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+              }
+              umma_commit(&empty[s]);    // frees the smem stage once these MMAs have read it
             }
-            umma_commit(&empty[s]);    // frees the smem stage once these MMAs have read it
+            __syncwarp();
           }
-          umma_commit(&tfull[buf]);    // segment complete -> drain warps
+          if (lane == 0) umma_commit(&tfull[buf]);    // segment complete -> drain warps
+          __syncwarp();
         }
+      }
+      if (p.dbg && lane == 0) {
+        p.dbg[blockIdx.x * 8 + 1] = w_split;
+        p.dbg[blockIdx.x * 8 + 2] = w_tempty;
       }
     }
   } else if (warp < 6) {
     // ================================ operand splitter ====================================
     const int t = threadIdx.x - 64;   // 0..127
     int it = 0;
+    long long w_full = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const TcChunk ck = p.chunk[item / p.ntiles];
       const int iters = ck.ksize * ck.ksize * p.kch;
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
-        mbar_wait(&full[s], ph);
+        SQ_TIMED_WAIT(w_full, &full[s], ph);
         float4* ahi = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES);
         float4* alo = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES + A_BYTES);
 #pragma unroll
@@ -336,12 +378,15 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         mbar_arrive(&split[s]);
       }
     }
+    if (p.dbg && t == 0) p.dbg[blockIdx.x * 8 + 3] = w_full;
   } else {
     // ============================ segment drain + epilogue ================================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                 // accumulator row = pixel within the tile
     float acc[MAX_N];
     int g = 0;
+    long long w_tfull = 0, c_epi = 0;
+    int n_item = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const TcChunk ck = p.chunk[item / p.ntiles];
       int tile = item % p.ntiles;
@@ -350,9 +395,21 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const int h0 = (tile % p.tiles_h) * TILE_H, w0 = tw * TILE_W, img = tile / p.tiles_h;
       const int iters = ck.ksize * ck.ksize * p.kch;
       const int ncols = (ck.ch_count + 15) & ~15;
+      // stage this item's bias / scale / shift in smem (one element per drain thread); the
+      // named barrier also orders it against the previous item's epilogue reads.
+      float* par = s_par + (n_item & 1) * 3 * MAX_N;
+      {
+        const int tt = threadIdx.x - 192;
+        const bool in = tt < ck.ch_count;
+        par[tt] = (in && p.bias) ? __ldg(p.bias + ck.bias_base + tt) : 0.f;
+        par[MAX_N + tt] = (in && p.scale) ? __ldg(p.scale + ck.bias_base + tt) : 1.f;
+        par[2 * MAX_N + tt] = (in && p.scale) ? __ldg(p.shift + ck.bias_base + tt) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      ++n_item;
       for (int i0 = 0; i0 < iters; i0 += G, ++g) {
         const int buf = g & 1;
-        mbar_wait(&tfull[buf], ((uint32_t)g >> 1) & 1u);
+        SQ_TIMED_WAIT(w_tfull, &tfull[buf], ((uint32_t)g >> 1) & 1u);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.N);
 #pragma unroll
@@ -377,35 +434,55 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         mbar_arrive(&tempty[buf]);               // buffer may be overwritten by segment g+2
       }
       // ---- epilogue: bias [, affine], relu, 128-bit stores of this pixel's channel run ----
+      const long long t_epi = p.dbg ? clock64() : 0;
       const int oh = h0 + (r >> 4), ow = w0 + (r & 15);
       if (oh < p.Ho && ow < p.Wo) {
         float* yrow =
             p.y + (((size_t)img * p.Ho + oh) * p.Wo + ow) * (size_t)p.y_cstride + ck.y_coff;
+        // 256-bit stores: each thread writes whole 32-byte sectors of its pixel's channel run.
+        // Branch-free per element: parameters come from smem (padded with bias 0 / scale 1).
+        const bool wide = ((p.y_cstride | ck.y_coff | ck.ch_count) & 7) == 0;
+        const bool affine = p.scale != nullptr;
+        const float lo_clip = p.relu ? 0.f : -CUDART_INF_F;
 #pragma unroll
-        for (int c = 0; c < MAX_N; c += 4) {
+        for (int c = 0; c < MAX_N; c += 8) {
           if (c < ck.ch_count) {
-            float o[4];
+            float o[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(par + c);
+            const float4 b1 = *reinterpret_cast<const float4*>(par + c + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float f = acc[c + e];
-              const int bi = ck.bias_base + c + e;
-              if (c + e < ck.ch_count) {
-                if (p.bias) f += __ldg(p.bias + bi);
-                if (p.scale) f = f * __ldg(p.scale + bi) + __ldg(p.shift + bi);
-              }
-              if (p.relu) f = fmaxf(f, 0.f);
-              o[e] = f;
+            for (int e = 0; e < 8; ++e) o[e] = acc[c + e] + bb[e];
+            if (affine) {
+              const float4 s0 = *reinterpret_cast<const float4*>(par + MAX_N + c);
+              const float4 s1 = *reinterpret_cast<const float4*>(par + MAX_N + c + 4);
+              const float4 h0v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c);
+              const float4 h1v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c + 4);
+              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float hh[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = o[e] * ss[e] + hh[e];
             }
-            if (c + 3 < ck.ch_count) {
-              *reinterpret_cast<float4*>(yrow + c) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], lo_clip);
+            if (wide) {
+              asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + c),
+                           "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
+                           "f"(o[6]), "f"(o[7])
+                           : "memory");
             } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
+              for (int e = 0; e < 8; ++e)
                 if (c + e < ck.ch_count) yrow[c + e] = o[e];
             }
           }
         }
       }
+      if (p.dbg) c_epi += clock64() - t_epi;
+    }
+    if (p.dbg && threadIdx.x == 192) {
+      p.dbg[blockIdx.x * 8 + 4] = w_tfull;
+      p.dbg[blockIdx.x * 8 + 7] = c_epi;
     }
   }
   tc_fence_before();
@@ -558,17 +635,37 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   P.nchunks = (int)im->chunks.size();
   for (int i = 0; i < P.nchunks; ++i) P.chunk[i] = im->chunks[i];
   const size_t stage = (size_t)2 * TILE_M * KC * 4 + (size_t)2 * N * KC * 4;
-  int stages = (int)((200 * 1024) / stage);
+  // Pipeline depth and residency: with two CTAs per SM (<= ~110 KB each) there are two
+  // independent TMA->split->MMA->drain pipelines per SM to hide latency; otherwise one deep one.
+  static int env_ctas = -1, env_stages = -1, env_seg = -1;
+  if (env_ctas < 0) {
+    const char* a = getenv("SQDET_TC_CTAS");   env_ctas = a ? atoi(a) : 0;
+    const char* b = getenv("SQDET_TC_STAGES"); env_stages = b ? atoi(b) : 0;
+    const char* c = getenv("SQDET_TC_SEG");    env_seg = c ? atoi(c) : 0;
+  }
+  int ctas = env_ctas > 0 ? env_ctas : 2;
+  const size_t overhead = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 3 * MAX_N * 4 /*epilogue params*/;
+  int stages = 0;
+  for (; ctas >= 1; --ctas) {
+    const size_t budget = (ctas == 1 ? 227 * 1024 : (227 * 1024) / ctas - 1024) - overhead;
+    stages = (int)(budget / stage);
+    if (stages >= 3 || ctas == 1) break;
+  }
+  if (ctas < 1) ctas = 1;
+  const int max_stages = env_stages > 0 ? env_stages : MAX_STAGES;
+  if (stages > max_stages) stages = max_stages;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return 0;
   P.stages = stages;
-  im->smem_bytes = stages * stage + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/;
+  if (env_seg > 0) P.seg_stages = env_seg;
+  im->smem_bytes = stages * stage + overhead;
   {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long items = (long long)P.ntiles * P.nchunks;
-    im->grid = dim3((unsigned)(items < sms ? items : sms));
+    const long long slots = (long long)sms * ctas;
+    im->grid = dim3((unsigned)(items < slots ? items : slots));
   }
   P.y = y_dev;
   SQ_CUDA(cudaMalloc(&im->d_w, sizeof(float) * (size_t)row * 2 * KC));
@@ -627,11 +724,39 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
   // the tensor map bakes in the activation address the plan was made for
   (void)x_dev;
   (void)y_dev;
+  static int debug = -1;
+  if (debug < 0) {
+    const char* d = getenv("SQDET_TC_DEBUG");
+    debug = d ? atoi(d) : 0;
+  }
+  TcParams prm = im->prm;
+  long long* dbg = nullptr;
+  const int nb = (int)im->grid.x;
+  if (debug) {
+    SQ_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * nb));
+    SQ_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * nb, stream));
+    prm.dbg = dbg;
+  }
   if (im->KC == 32)
-    conv_tc_kernel<32><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(im->prm);
+    conv_tc_kernel<32><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
   else
-    conv_tc_kernel<16><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(im->prm);
+    conv_tc_kernel<16><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
   SQ_CHECK_LAUNCH("conv_tc_kernel");
+  if (debug) {
+    std::vector<long long> h((size_t)8 * nb);
+    SQ_CUDA(cudaStreamSynchronize(stream));
+    SQ_CUDA(cudaMemcpy(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    double a[8] = {0};
+    for (int b = 0; b < nb; ++b)
+      for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)b * 8 + k] / nb;
+    fprintf(stderr,
+            "[tc] grid %d smem %zu KC %d N %d kch %d chunks %d stages %d seg %d | per-CTA avg cycles: "
+            "total %.0f stages %.0f | waits: producer(empty) %.0f mma(split) %.0f mma(tempty) %.0f "
+            "splitter(full) %.0f drain(tfull) %.0f | epilogue %.0f\n",
+            nb, im->smem_bytes, im->KC, prm.N, prm.kch, prm.nchunks, prm.stages, prm.seg_stages,
+            a[5], a[6], a[0], a[1], a[2], a[3], a[4], a[7]);
+  }
   return SQDET_OK;
 }
 
