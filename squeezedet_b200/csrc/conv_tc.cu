@@ -72,6 +72,7 @@ struct TcChunk {
 struct TcParams {
   CUtensorMap tmA;
   CUtensorMap tmW;
+  CUtensorMap tmY;      // output tensor, box {32 ch, 16 w, 8 h, 1}, SWIZZLE_128B (TMA-store epilogue)
   const float* bias;    // may be null
   const float* scale;   // may be null (frozen BN)
   const float* shift;
@@ -82,6 +83,7 @@ struct TcParams {
   int tmem_cols;        // power of two >= max(32, 2*N): two accumulator buffers
   int seg_stages;       // pipeline stages (K blocks) per accumulation segment
   int ntiles;           // B * tiles_h * tiles_w
+  int tma_store;        // 1: epilogue stages 32-channel groups in smem and issues TMA stores
   long long* dbg;       // optional per-CTA cycle counters (SQDET_TC_DEBUG=1), else null
   int y_cstride, relu;
   int lo_row_offset;    // rows between the hi and the lo copy of the packed weights
@@ -134,6 +136,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap* map, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read_le1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -237,6 +253,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   // per-item epilogue parameters (bias, scale, shift), double-buffered by item parity
   float* s_par = reinterpret_cast<float*>(tempty + 4);   // [2][3][MAX_N]
+  // two 16 KB output staging tiles (128 pixels x 32 channels, 128B-swizzled) for TMA stores
+  uint8_t* s_out = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(s_par + 2 * 3 * MAX_N) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_items = p.ntiles * p.nchunks;
@@ -395,7 +414,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     float acc[MAX_N];
     int g = 0;
     long long w_tfull = 0, c_epi = 0;
-    int n_item = 0;
+    int n_item = 0, n_store = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const TcChunk ck = p.chunk[item / p.ntiles];
       int tile = item % p.ntiles;
@@ -445,7 +464,42 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       // ---- epilogue: bias [, affine], relu, 128-bit stores of this pixel's channel run ----
       const long long t_epi = p.dbg ? clock64() : 0;
       const int oh = h0 + (r >> 4), ow = w0 + (r & 15);
-      if (oh < p.Ho && ow < p.Wo) {
+      if (p.tma_store) {
+        // TMEM-drained sums -> (+bias [*scale+shift], relu) -> swizzled smem tile -> TMA store.
+        // The TMA unit writes whole 128-byte lines asynchronously and clips ragged tiles and
+        // the channel tail; the drain warps never wait on global memory.
+        const bool affine = p.scale != nullptr;
+        const float lo_clip = p.relu ? 0.f : -CUDART_INF_F;
+        const bool issuer = threadIdx.x == 256;
+#pragma unroll
+        for (int jg = 0; jg < MAX_N / 32; ++jg) {
+          if (jg * 32 < ck.ch_count) {                    // warp-uniform
+            if (issuer) tma_store_wait_read_le1();        // the tile used 2 stores ago is free
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            uint8_t* tile = s_out + (n_store & 1) * 16384;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int c = jg * 32 + k * 4;
+              const float4 b0 = *reinterpret_cast<const float4*>(par + c);
+              float o[4] = {acc[c] + b0.x, acc[c + 1] + b0.y, acc[c + 2] + b0.z, acc[c + 3] + b0.w};
+              if (affine) {
+                const float4 s0 = *reinterpret_cast<const float4*>(par + MAX_N + c);
+                const float4 h0v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c);
+                o[0] = o[0] * s0.x + h0v.x; o[1] = o[1] * s0.y + h0v.y;
+                o[2] = o[2] * s0.z + h0v.z; o[3] = o[3] * s0.w + h0v.w;
+              }
+              float4 v;
+              v.x = fmaxf(o[0], lo_clip); v.y = fmaxf(o[1], lo_clip);
+              v.z = fmaxf(o[2], lo_clip); v.w = fmaxf(o[3], lo_clip);
+              *reinterpret_cast<float4*>(tile + r * 128 + ((k ^ (r & 7)) << 4)) = v;
+            }
+            fence_async_proxy();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (issuer) tma_store_4d(tile, &p.tmY, ck.y_coff + jg * 32, w0, h0, img);
+            ++n_store;
+          }
+        }
+      } else if (oh < p.Ho && ow < p.Wo) {
         float* yrow =
             p.y + (((size_t)img * p.Ho + oh) * p.Wo + ow) * (size_t)p.y_cstride + ck.y_coff;
         // 256-bit stores: each thread writes whole 32-byte sectors of its pixel's channel run.
@@ -489,6 +543,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
       if (p.dbg) c_epi += clock64() - t_epi;
     }
+    if (p.tma_store && threadIdx.x == 256) tma_store_wait_all();
     if (p.dbg && threadIdx.x == 256) {
       p.dbg[blockIdx.x * 8 + 4] = w_tfull;
       p.dbg[blockIdx.x * 8 + 7] = c_epi;
@@ -653,7 +708,8 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     const char* c = getenv("SQDET_TC_SEG");    env_seg = c ? atoi(c) : 0;
   }
   int ctas = env_ctas > 0 ? env_ctas : 2;
-  const size_t overhead = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 3 * MAX_N * 4 /*epilogue params*/;
+  const size_t overhead = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 3 * MAX_N * 4 /*epilogue params*/ +
+                          1024 + 2 * 16384 /*TMA-store staging tiles*/;
   int stages = 0;
   for (; ctas >= 1; --ctas) {
     const size_t budget = (ctas == 1 ? 227 * 1024 : (227 * 1024) / ctas - 1024) - overhead;
@@ -690,6 +746,25 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   }
   int rc = encode_act_map(&P.tmA, x_dev, B, H, W, Cin, KC);
   if (rc) return rc;
+  // TMA-store epilogue: needs every chunk to be a whole number of 32-channel groups unless it
+  // ends at the tensor's last channel (where the TMA unit clips the tail).
+  {
+    static int env_tma = -1;
+    if (env_tma < 0) {
+      const char* a = getenv("SQDET_TC_TMA_STORE");
+      env_tma = a ? atoi(a) : 1;
+    }
+    bool ok = env_tma != 0 && (y_cstride % 4 == 0);
+    for (auto& c : im->chunks)
+      if ((c.ch_count % 32) != 0 && (c.y_coff + c.ch_count != y_cstride)) ok = false;
+    for (auto& c : im->chunks)
+      if (c.y_coff % 4 != 0) ok = false;
+    if (ok) {
+      rc = encode_act_map(&P.tmY, y_dev, B, H, W, y_cstride, 32);
+      if (rc) return rc;
+    }
+    P.tma_store = ok ? 1 : 0;
+  }
   rc = encode_w_map(&P.tmW, im->d_w, row * 2, KC, N);
   if (rc) return rc;
   // opt in to the full 227 KB once for both instantiations (the attribute is per function,
