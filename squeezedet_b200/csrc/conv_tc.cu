@@ -57,7 +57,7 @@ constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;   // 128 pixels
 constexpr int NUM_THREADS = 384;       // 3 warpgroups: {TMA, MMA, 2 spare} | splitter | drain
 constexpr int MAX_CHUNKS = 16;
 constexpr int MAX_N = 128;          // output channels per item (register-resident running sums)
-constexpr int MAX_STAGES = 12;
+constexpr int MAX_STAGES = 8;
 
 struct TcChunk {
   int ksize;        // 1 or 3 (square)
@@ -227,6 +227,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     }                                                       \
   } while (0)
 
+// elect.sync: exactly one lane of the (converged) warp gets true; lets ptxas predicate the
+// single-issuer tcgen05 instructions without a divergence waterfall.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float rn_tf32(float x) {
   // round-to-nearest (ties away) onto the 10-bit TF32 mantissa; low 13 bits end up zero so
   // the value is exact whatever rounding the tensor core applies to its fp32 inputs.
@@ -288,7 +302,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
    if (warp == 0) {
     // ================================ TMA producer =====================================
     if (lane == 0) {
-      int it = 0;
+      int it = 0, st_i = 0;
+      uint32_t st_ph = 0;
       long long w_empty = 0;
       const long long t_begin = clock64();
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -299,8 +314,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const int h0 = (tile % p.tiles_h) * TILE_H, w0 = tw * TILE_W, img = tile / p.tiles_h;
         const int iters = ck.ksize * ck.ksize * p.kch;
         for (int i = 0; i < iters; ++i, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          const int s = st_i;
+          const uint32_t ph = st_ph;
+          if (++st_i == S) { st_i = 0; st_ph ^= 1u; }
           SQ_TIMED_WAIT(w_empty, &empty[s], ph ^ 1u);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
           mbar_expect_tx(&full[s], (uint32_t)(A_BYTES + 2 * B_BYTES));
@@ -329,7 +345,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
       const uint64_t desc_hi = make_desc<KC>(0) & 0xFFFFFFFF00000000ull;   // layout/SBO/version
       const uint32_t desc_lo0 = (uint32_t)(make_desc<KC>(0) & 0xFFFFFFFFull);  // LBO field
-      int it = 0, g = 0;
+      int it = 0, g = 0, st_i = 0;
+      uint32_t st_ph = 0;
       long long w_split = 0, w_tempty = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const TcChunk ck = p.chunk[item / p.ntiles];
@@ -341,8 +358,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           const uint32_t d_tmem = tmem_u + (uint32_t)(buf * p.N);
           const int i1 = (i0 + G < iters) ? (i0 + G) : iters;
           for (int i = i0; i < i1; ++i, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            const int s = st_i;
+            const uint32_t ph = st_ph;
+            if (++st_i == S) { st_i = 0; st_ph ^= 1u; }
             SQ_TIMED_WAIT(w_split, &split[s], ph);
             tc_fence_after();
             // descriptor low words (start address >> 4 | LBO); +2 per 32-byte K step
@@ -350,7 +368,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             const uint32_t a_lo = a_hi + (A_BYTES >> 4);
             const uint32_t b_hi = a_hi + (2 * A_BYTES >> 4);
             const uint32_t b_lo = b_hi + (uint32_t)(B_BYTES >> 4);
-            if (lane == 0) {
+            if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < KC / 8; ++j) {
                 const uint64_t dah = desc_hi | (uint64_t)(a_hi + 2 * j);
@@ -365,7 +383,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             }
             __syncwarp();
           }
-          if (lane == 0) umma_commit(&tfull[buf]);    // segment complete -> drain warps
+          if (elect_one()) umma_commit(&tfull[buf]);    // segment complete -> drain warps
           __syncwarp();
         }
       }
@@ -379,14 +397,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     // ================================ operand splitter ====================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     const int t = threadIdx.x - 128;   // 0..127
-    int it = 0;
+    int it = 0, st_i = 0;
+    uint32_t st_ph = 0;
     long long w_full = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const TcChunk ck = p.chunk[item / p.ntiles];
       const int iters = ck.ksize * ck.ksize * p.kch;
       for (int i = 0; i < iters; ++i, ++it) {
-        const int s = it % S;
-        const uint32_t ph = (uint32_t)(it / S) & 1u;
+        const int s = st_i;
+        const uint32_t ph = st_ph;
+        if (++st_i == S) { st_i = 0; st_ph ^= 1u; }
         SQ_TIMED_WAIT(w_full, &full[s], ph);
         float4* ahi = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES);
         float4* alo = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES + A_BYTES);
@@ -707,7 +727,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     const char* b = getenv("SQDET_TC_STAGES"); env_stages = b ? atoi(b) : 0;
     const char* c = getenv("SQDET_TC_SEG");    env_seg = c ? atoi(c) : 0;
   }
-  int ctas = env_ctas > 0 ? env_ctas : 2;
+  int ctas = env_ctas > 0 ? env_ctas : 1;   // 384 threads x 168 regs: one CTA per SM
   const size_t overhead = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 3 * MAX_N * 4 /*epilogue params*/ +
                           1024 + 2 * 16384 /*TMA-store staging tiles*/;
   int stages = 0;
