@@ -18,8 +18,12 @@
 //   a_lo = rn_tf32(a - a_hi); D += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation
 //   in TMEM (kind::tf32).  Dropped term a_lo*b_lo ~ 2^-22: fp32-grade results, which the
 //   1e-4 parity bar against the fp32 reference needs through ~25 stacked convs (plain TF32
-//   or BF16 miss it by 1-2 orders of magnitude).  The activation split runs in shared
-//   memory (4 warps) between the TMA landing and the MMA issue; weights are pre-split.
+//   or BF16 miss it by 1-2 orders of magnitude).  Weights are pre-split on the host.  The
+//   activation split is done by 4 warps between the TMA landing and the MMA issue: each thread
+//   reads its pixel's row of the raw tile from smem and writes a_hi / a_lo into TENSOR MEMORY
+//   (tcgen05.st); the MMAs take A from TMEM (.ts form) and only B from smem.  (With A in smem
+//   the kernel was shared-memory-bandwidth bound: 3 MMAs x (128+N) x 32 B per K step plus the
+//   splitter's own traffic ~ 2x the 128 B/clk/SM the SM has; measured, see DESIGN.md.)
 // Accumulation: the tensor core adds into its fp32 accumulator with truncation (measured
 //   on B200: error grows linearly with the number of chained MMAs, 3.6e-5 of max at K=6912
 //   vs 2e-6 for fp32 FFMA).  So a tile's K loop is cut into SEGMENTS of ~24 MMAs, each
@@ -80,7 +84,7 @@ struct TcParams {
   int B, Ho, Wo, tiles_h, tiles_w;
   int kch;              // Cin / KC
   int N;                // UMMA N (uniform over chunks)
-  int tmem_cols;        // power of two >= max(32, 2*N): two accumulator buffers
+  int tmem_cols;        // power of two >= 2*N (two accumulator buffers) + stages*2*KC (A slots)
   int seg_stages;       // pipeline stages (K blocks) per accumulation segment
   int ntiles;           // B * tiles_h * tiles_w
   int tma_store;        // 1: epilogue stages 32-channel groups in smem and issues TMA stores
@@ -171,17 +175,29 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void fence_async_proxy() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, single CTA.
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// 16 consecutive TMEM columns of this warp's 32 lanes <- 16 registers per thread
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -256,7 +272,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                                              ~uintptr_t(1023));
   constexpr int A_BYTES = TILE_M * KC * 4;
   const int B_BYTES = p.N * KC * 4;
-  const int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  const int STAGE_BYTES = A_BYTES + 2 * B_BYTES;   // [A raw][B hi][B lo]
   const int S = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * STAGE_BYTES);
   uint64_t* full = bars;                    // [S]  TMA -> splitter
@@ -324,8 +340,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           const int dy = tap / ck.ksize, dx = tap - dy * ck.ksize;
           tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
           const int row = ck.w_row_base + i * p.N;
-          tma_load_2d(st + 2 * A_BYTES, &p.tmW, &full[s], 0, row);
-          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &p.tmW, &full[s], 0, row + p.lo_row_offset);
+          tma_load_2d(st + A_BYTES, &p.tmW, &full[s], 0, row);
+          tma_load_2d(st + A_BYTES + B_BYTES, &p.tmW, &full[s], 0, row + p.lo_row_offset);
         }
       }
       if (p.dbg) {
@@ -363,21 +379,21 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             if (++st_i == S) { st_i = 0; st_ph ^= 1u; }
             SQ_TIMED_WAIT(w_split, &split[s], ph);
             tc_fence_after();
-            // descriptor low words (start address >> 4 | LBO); +2 per 32-byte K step
-            const uint32_t a_hi = desc_lo0 | ((smem_base + (uint32_t)(s * STAGE_BYTES)) >> 4);
-            const uint32_t a_lo = a_hi + (A_BYTES >> 4);
-            const uint32_t b_hi = a_hi + (2 * A_BYTES >> 4);
+            // B descriptor low words (start address >> 4 | LBO), +2 per 32-byte K step;
+            // A operand: TMEM slot s = 2*KC columns [hi | lo], 8 columns per K step
+            const uint32_t b_hi =
+                desc_lo0 | ((smem_base + (uint32_t)(s * STAGE_BYTES) + (uint32_t)A_BYTES) >> 4);
             const uint32_t b_lo = b_hi + (uint32_t)(B_BYTES >> 4);
+            const uint32_t a_hi = tmem_u + (uint32_t)(2 * p.N + s * 2 * KC);
+            const uint32_t a_lo = a_hi + KC;
             if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < KC / 8; ++j) {
-                const uint64_t dah = desc_hi | (uint64_t)(a_hi + 2 * j);
-                const uint64_t dal = desc_hi | (uint64_t)(a_lo + 2 * j);
                 const uint64_t dbh = desc_hi | (uint64_t)(b_hi + 2 * j);
                 const uint64_t dbl = desc_hi | (uint64_t)(b_lo + 2 * j);
-                umma_tf32(d_tmem, dal, dbh, idesc, (i != i0 || j != 0) ? 1u : 0u);
-                umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                umma_tf32_ts(d_tmem, a_lo + 8 * j, dbh, idesc, (i != i0 || j != 0) ? 1u : 0u);
+                umma_tf32_ts(d_tmem, a_hi + 8 * j, dbl, idesc, 1u);
+                umma_tf32_ts(d_tmem, a_hi + 8 * j, dbh, idesc, 1u);
               }
               umma_commit(&empty[s]);    // frees the smem stage once these MMAs have read it
             }
@@ -408,20 +424,32 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const uint32_t ph = st_ph;
         if (++st_i == S) { st_i = 0; st_ph ^= 1u; }
         SQ_TIMED_WAIT(w_full, &full[s], ph);
-        float4* ahi = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES);
-        float4* alo = reinterpret_cast<float4*>(smem + (size_t)s * STAGE_BYTES + A_BYTES);
+        // row t of the raw tile (KC*4 bytes, swizzled 16-byte chunks) -> registers ->
+        // a_hi / a_lo -> TMEM slot s, lane t (this warp owns lanes 32*(warp%4)..+31)
+        const uint8_t* arow = smem + (size_t)s * STAGE_BYTES + (size_t)t * (KC * 4);
+        const int sw = (KC == 32) ? (t & 7) : ((t >> 1) & 3);
+        const uint32_t a_slot = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
+                                (uint32_t)(2 * p.N + s * 2 * KC);
 #pragma unroll
-        for (int k = 0; k < A_BYTES / 16 / 128; ++k) {
-          const int idx = k * 128 + t;
-          const float4 v = ahi[idx];
-          float4 h, l;
-          h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
-          l.x = rn_tf32(v.x - h.x); l.y = rn_tf32(v.y - h.y);
-          l.z = rn_tf32(v.z - h.z); l.w = rn_tf32(v.w - h.w);
-          ahi[idx] = h;
-          alo[idx] = l;
+        for (int hblk = 0; hblk < KC / 16; ++hblk) {       // 16 columns at a time
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int chunk = hblk * 4 + k;
+            const float4 v = *reinterpret_cast<const float4*>(arow + ((chunk ^ sw) << 4));
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float h = rn_tf32(vv[e]);
+              hi[k * 4 + e] = __float_as_uint(h);
+              lo[k * 4 + e] = __float_as_uint(rn_tf32(vv[e] - h));
+            }
+          }
+          tmem_st16(a_slot + (uint32_t)(hblk * 16), hi);
+          tmem_st16(a_slot + (uint32_t)(KC + hblk * 16), lo);
         }
-        fence_async_proxy();           // generic-proxy stores -> visible to the tensor core
+        tmem_wait_st();
+        tc_fence_before();             // order the TMEM writes before the barrier hand-off
         mbar_arrive(&split[s]);
       }
     }
@@ -707,9 +735,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   P.tiles_w = (W + TILE_W - 1) / TILE_W;
   P.kch = kch;
   P.N = N;
-  int cols = 32;
-  while (cols < 2 * N) cols <<= 1;
-  P.tmem_cols = cols;
+
   // ~24 chained MMAs per accumulation segment (3 MMAs per 8-wide K step)
   P.seg_stages = (KC == 32) ? 2 : 4;
   P.ntiles = B * P.tiles_h * P.tiles_w;
@@ -718,7 +744,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   P.lo_row_offset = row;
   P.nchunks = (int)im->chunks.size();
   for (int i = 0; i < P.nchunks; ++i) P.chunk[i] = im->chunks[i];
-  const size_t stage = (size_t)2 * TILE_M * KC * 4 + (size_t)2 * N * KC * 4;
+  const size_t stage = (size_t)TILE_M * KC * 4 + (size_t)2 * N * KC * 4;
   // Pipeline depth and residency: with two CTAs per SM (<= ~110 KB each) there are two
   // independent TMA->split->MMA->drain pipelines per SM to hide latency; otherwise one deep one.
   static int env_ctas = -1, env_stages = -1, env_seg = -1;
@@ -740,8 +766,15 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   const int max_stages = env_stages > 0 ? env_stages : MAX_STAGES;
   if (stages > max_stages) stages = max_stages;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) return 0;
+  // TMEM: two accumulator buffers (2N columns) + one [a_hi | a_lo] slot (2*KC columns) per stage
+  while (stages > 2 && 2 * N + stages * 2 * KC > 512) --stages;
+  if (stages < 2 || 2 * N + stages * 2 * KC > 512) return 0;
   P.stages = stages;
+  {
+    int cols = 32;
+    while (cols < 2 * N + stages * 2 * KC) cols <<= 1;
+    P.tmem_cols = cols;
+  }
   if (env_seg > 0) P.seg_stages = env_seg;
   im->smem_bytes = stages * stage + overhead;
   {
