@@ -35,6 +35,16 @@ def make_mc(net, width, height, batch):
   return mc
 
 
+def assert_boxes_close(got, ref32, ref64):
+  """Box coordinates: within 1e-4 relative of the fp32 reference, plus the reference's OWN
+  fp32 uncertainty (|ref32 - ref64|, x4) — boxes that clip from ~4000 px wide pre-clip values
+  carry ~1e-3 px of fp32 rounding in any implementation — plus 1e-3 px absolute."""
+  got = np.asarray(got, np.float64)
+  tol = TOL * np.abs(ref32) + 4.0 * np.abs(np.asarray(ref32, np.float64) - ref64) + 1e-3
+  bad = np.abs(got - ref32) > tol
+  assert not bad.any(), (int(bad.sum()), float(np.abs(got - ref32)[bad].max()))
+
+
 def oracle_run(net, mc, weights, images, dtype=np.float32, keep=None):
   preds = oracle.forward(net, weights, images, dtype=dtype, keep=keep)
   return preds, oracle.interpret_output(preds, mc.ANCHOR_BOX, mc.CLASSES, mc.ANCHOR_PER_GRID,
@@ -69,7 +79,7 @@ def test_layerwise_parity_small_image(net, width, height, math_mode, gpu_device)
       checked += 1
   assert checked >= 10
   np.testing.assert_allclose(probs, s32, rtol=TOL, atol=1e-7)
-  np.testing.assert_allclose(boxes, b32, rtol=TOL, atol=1e-3)
+  assert_boxes_close(boxes, b32, b64)
   assert (cls != c32).mean() < 1e-3
 
 
@@ -86,10 +96,11 @@ def test_full_size_squeezedet_detections(math_mode, gpu_device):
   model.load_weights(weights)
   images = synth.synthetic_images(2, 375, 1242, seed=1234)
   _, (wb, wp, wc) = oracle_run(net, mc, weights, images, np.float32)
+  _, (wb64, _, _) = oracle_run(net, mc, weights, images, np.float64)
   boxes, probs, cls, dets, counts = model.detect(images, want_dets=True)
   assert boxes.dtype == np.float32 and probs.dtype == np.float32 and cls.dtype == np.int64
   np.testing.assert_allclose(probs, wp, rtol=TOL, atol=1e-7)
-  np.testing.assert_allclose(boxes, wb, rtol=TOL, atol=1e-3)
+  assert_boxes_close(boxes, wb, wb64)
   assert (cls != wc).mean() < 1e-3
   for i in range(2):
     # (1) bit-exact: GPU filter on the GPU's own det tensors == oracle filter on them
