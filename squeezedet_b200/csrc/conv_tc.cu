@@ -88,6 +88,11 @@ struct TcParams {
   int seg_stages;       // pipeline stages (K blocks) per accumulation segment
   int ntiles;           // B * tiles_h * tiles_w
   int tma_store;        // 1: epilogue stages 32-channel groups in smem and issues TMA stores
+  // conv tile (rows of the M=128 MMA tile): ct_h x ct_w output pixels (8x16, or 7x17 / 8x16
+  // when a 3x3 / 2x2 stride-2 max-pool is fused into the epilogue); tile step in conv pixels
+  int ct_h, ct_w, step_h, step_w, org_h, org_w;   // origin = tile*step - org
+  // fused max-pool (0 = none, else window 2 or 3; stride 2): pooled tile pt_h x pt_w, pooled dims
+  int pool, pt_h, pt_w, Hp, Wp;
   long long* dbg;       // optional per-CTA cycle counters (SQDET_TC_DEBUG=1), else null
   int y_cstride, relu;
   int lo_row_offset;    // rows between the hi and the lo copy of the packed weights
@@ -327,15 +332,17 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         int tile = item % p.ntiles;
         const int tw = tile % p.tiles_w;
         tile /= p.tiles_w;
-        const int h0 = (tile % p.tiles_h) * TILE_H, w0 = tw * TILE_W, img = tile / p.tiles_h;
+        const int h0 = (tile % p.tiles_h) * p.step_h - p.org_h, w0 = tw * p.step_w - p.org_w;
+        const int img = tile / p.tiles_h;
         const int iters = ck.ksize * ck.ksize * p.kch;
+        const uint32_t a_bytes = (uint32_t)(p.ct_h * p.ct_w * KC * 4);   // the TMA box
         for (int i = 0; i < iters; ++i, ++it) {
           const int s = st_i;
           const uint32_t ph = st_ph;
           if (++st_i == S) { st_i = 0; st_ph ^= 1u; }
           SQ_TIMED_WAIT(w_empty, &empty[s], ph ^ 1u);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-          mbar_expect_tx(&full[s], (uint32_t)(A_BYTES + 2 * B_BYTES));
+          mbar_expect_tx(&full[s], a_bytes + (uint32_t)(2 * B_BYTES));
           const int tap = i / p.kch, kc = i - tap * p.kch;
           const int dy = tap / ck.ksize, dx = tap - dy * ck.ksize;
           tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
@@ -468,7 +475,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       int tile = item % p.ntiles;
       const int tw = tile % p.tiles_w;
       tile /= p.tiles_w;
-      const int h0 = (tile % p.tiles_h) * TILE_H, w0 = tw * TILE_W, img = tile / p.tiles_h;
+      const int th_i = tile % p.tiles_h;
+      const int h0 = th_i * p.step_h - p.org_h, w0 = tw * p.step_w - p.org_w;
+      const int img = tile / p.tiles_h;
       const int iters = ck.ksize * ck.ksize * p.kch;
       const int ncols = (ck.ch_count + 15) & ~15;
       // stage this item's bias / scale / shift in smem (one element per drain thread); the
@@ -511,7 +520,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
       // ---- epilogue: bias [, affine], relu, 128-bit stores of this pixel's channel run ----
       const long long t_epi = p.dbg ? clock64() : 0;
-      const int oh = h0 + (r >> 4), ow = w0 + (r & 15);
+      const int r_h = r / p.ct_w, r_w = r - r_h * p.ct_w;
+      const int oh = h0 + r_h, ow = w0 + r_w;
+      const bool pix_ok = (r_h < p.ct_h) && oh >= 0 && ow >= 0 && oh < p.Ho && ow < p.Wo;
       if (p.tma_store) {
         // TMEM-drained sums -> (+bias [*scale+shift], relu) -> swizzled smem tile -> TMA store.
         // The TMA unit writes whole 128-byte lines asynchronously and clips ragged tiles and
@@ -519,12 +530,15 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const bool affine = p.scale != nullptr;
         const float lo_clip = p.relu ? 0.f : -CUDART_INF_F;
         const bool issuer = threadIdx.x == 256;
+        const int tt = threadIdx.x - 256;
 #pragma unroll
         for (int jg = 0; jg < MAX_N / 32; ++jg) {
           if (jg * 32 < ck.ch_count) {                    // warp-uniform
             if (issuer) tma_store_wait_read_le1();        // the tile used 2 stores ago is free
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            uint8_t* tile = s_out + (n_store & 1) * 16384;
+            // conv staging tile: without pooling it IS the TMA-store source (double-buffered);
+            // with pooling it is tile 0 and the pooled tiles live behind it.
+            uint8_t* tile_c = p.pool ? s_out : s_out + (n_store & 1) * 16384;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const int c = jg * 32 + k * 4;
@@ -539,15 +553,43 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               float4 v;
               v.x = fmaxf(o[0], lo_clip); v.y = fmaxf(o[1], lo_clip);
               v.z = fmaxf(o[2], lo_clip); v.w = fmaxf(o[3], lo_clip);
-              *reinterpret_cast<float4*>(tile + r * 128 + ((k ^ (r & 7)) << 4)) = v;
+              if (p.pool && !pix_ok)      // tf.nn.max_pool ignores cells outside the image
+                v = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+              *reinterpret_cast<float4*>(tile_c + r * 128 + ((k ^ (r & 7)) << 4)) = v;
             }
-            fence_async_proxy();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (issuer) tma_store_4d(tile, &p.tmY, ck.y_coff + jg * 32, w0, h0, img);
+            if (!p.pool) {
+              fence_async_proxy();
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (issuer) tma_store_4d(tile_c, &p.tmY, ck.y_coff + jg * 32, w0, h0, img);
+            } else {
+              // fused tf.nn.max_pool (window p.pool, stride 2): pooled pixel pp of the tile,
+              // 16-byte channel chunk k2 -> max over the window's conv-tile rows
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              uint8_t* tile_p = s_out + 16384 + (n_store & 1) * 4096;
+              const int n_pp = p.pt_h * p.pt_w;
+              for (int u = tt; u < n_pp * 8; u += 128) {
+                const int pp = u >> 3, k2 = u & 7;
+                const int py = pp / p.pt_w, px = pp - py * p.pt_w;
+                float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+                for (int a = 0; a < p.pool; ++a)
+                  for (int b = 0; b < p.pool; ++b) {
+                    const int rr = (2 * py + a) * p.ct_w + 2 * px + b;
+                    const float4 q4 = *reinterpret_cast<const float4*>(
+                        s_out + rr * 128 + ((k2 ^ (rr & 7)) << 4));
+                    m.x = fmaxf(m.x, q4.x); m.y = fmaxf(m.y, q4.y);
+                    m.z = fmaxf(m.z, q4.z); m.w = fmaxf(m.w, q4.w);
+                  }
+                *reinterpret_cast<float4*>(tile_p + pp * 128 + ((k2 ^ (pp & 7)) << 4)) = m;
+              }
+              fence_async_proxy();
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (issuer)
+                tma_store_4d(tile_p, &p.tmY, ck.y_coff + jg * 32, tw * p.pt_w, th_i * p.pt_h, img);
+            }
             ++n_store;
           }
         }
-      } else if (oh < p.Ho && ow < p.Wo) {
+      } else if (pix_ok) {
         float* yrow =
             p.y + (((size_t)img * p.Ho + oh) * p.Wo + ow) * (size_t)p.y_cstride + ck.y_coff;
         // 256-bit stores: each thread writes whole 32-byte sectors of its pixel's channel run.
@@ -654,12 +696,13 @@ static inline float host_rn_tf32(float x) {
   return r;
 }
 
-static int encode_act_map(CUtensorMap* map, const float* x, int B, int H, int W, int C, int KC) {
+static int encode_act_map(CUtensorMap* map, const float* x, int B, int H, int W, int C, int KC,
+                          int box_w = TILE_W, int box_h = TILE_H) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(SQDET_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {(cuuint32_t)KC, TILE_W, TILE_H, 1};
+  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -694,7 +737,8 @@ static int encode_w_map(CUtensorMap* map, const float* w, int rows, int KC, int 
 
 // Common planner: `groups` convs (same ksize rules as the fire pair) over one input.
 static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vector<ConvGroup>& groups,
-                       int relu, bool has_affine, int y_cstride, const float* x_dev, float* y_dev) {
+                       int relu, bool has_affine, int y_cstride, const float* x_dev, float* y_dev,
+                       const TcPool* pool) {
   im->Cin = Cin;
   im->KC = (Cin % 32 == 0) ? 32 : 16;
   const int KC = im->KC;
@@ -731,8 +775,25 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   im->bias_total = 0;
   for (auto& g : groups) im->bias_total = (g.bias_base + g.Cout) > im->bias_total ? (g.bias_base + g.Cout) : im->bias_total;
   P.B = B; P.Ho = H; P.Wo = W;                      // stride-1 SAME: output grid == input grid
+  P.ct_h = TILE_H; P.ct_w = TILE_W; P.step_h = TILE_H; P.step_w = TILE_W;
+  P.org_h = P.org_w = 0;
   P.tiles_h = (H + TILE_H - 1) / TILE_H;
   P.tiles_w = (W + TILE_W - 1) / TILE_W;
+  const bool pooled = pool && pool->size > 0;
+  if (pooled) {
+    // conv tile = the conv pixels under a pt_h x pt_w block of stride-2 pooling windows
+    if (pool->size != 2 && pool->size != 3) return 0;
+    P.pool = pool->size;
+    P.pt_h = pool->size == 3 ? 3 : 4;
+    P.pt_w = 8;
+    P.ct_h = 2 * (P.pt_h - 1) + pool->size;      // 7 or 8
+    P.ct_w = 2 * (P.pt_w - 1) + pool->size;      // 17 or 16
+    P.step_h = 2 * P.pt_h; P.step_w = 2 * P.pt_w;
+    P.org_h = pool->pad_t; P.org_w = pool->pad_l;
+    P.Hp = pool->Hp; P.Wp = pool->Wp;
+    P.tiles_h = (pool->Hp + P.pt_h - 1) / P.pt_h;
+    P.tiles_w = (pool->Wp + P.pt_w - 1) / P.pt_w;
+  }
   P.kch = kch;
   P.N = N;
 
@@ -797,7 +858,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     P.scale = im->d_scale;
     P.shift = im->d_shift;
   }
-  int rc = encode_act_map(&P.tmA, x_dev, B, H, W, Cin, KC);
+  int rc = encode_act_map(&P.tmA, x_dev, B, H, W, Cin, KC, P.ct_w, P.ct_h);
   if (rc) return rc;
   // TMA-store epilogue: needs every chunk to be a whole number of 32-channel groups unless it
   // ends at the tensor's last channel (where the TMA unit clips the tail).
@@ -812,8 +873,12 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
       if ((c.ch_count % 32) != 0 && (c.y_coff + c.ch_count != y_cstride)) ok = false;
     for (auto& c : im->chunks)
       if (c.y_coff % 4 != 0) ok = false;
+    if (pooled && !ok) return 0;          // the fused pool exists only on the TMA-store path
     if (ok) {
-      rc = encode_act_map(&P.tmY, y_dev, B, H, W, y_cstride, 32);
+      if (pooled)
+        rc = encode_act_map(&P.tmY, y_dev, B, pool->Hp, pool->Wp, y_cstride, 32, P.pt_w, P.pt_h);
+      else
+        rc = encode_act_map(&P.tmY, y_dev, B, H, W, y_cstride, 32);
       if (rc) return rc;
     }
     P.tma_store = ok ? 1 : 0;
@@ -911,16 +976,41 @@ static void release_impl(void** impl) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+bool tc_conv_eligible(int Cin, int Cout, int size, int stride, int padding, int y_cstride,
+                      int y_coff) {
+  // shapes this path takes: stride-1 SAME, 1x1 or 3x3, Cin a multiple of 16, 16B-aligned stores
+  if (stride != 1 || padding != SQDET_PAD_SAME || (size != 1 && size != 3)) return false;
+  if (Cin % 16 != 0 || Cin < 16 || (y_cstride % 4) || (y_coff % 4) || (Cout % 4)) return false;
+  return true;
+}
+
+bool tc_pool_fusable(const int* couts, const int* coffs, int ngroups, int y_cstride, int pool_size,
+                     int pool_stride) {
+  // mirrors plan_common: uniform chunk width N; every chunk must be whole 32-channel groups
+  // unless it ends the output tensor (TMA clips the tail there)
+  if ((pool_size != 2 && pool_size != 3) || pool_stride != 2 || (y_cstride % 4)) return false;
+  int maxc = 0;
+  for (int g = 0; g < ngroups; ++g) maxc = couts[g] > maxc ? couts[g] : maxc;
+  const int nsplit = (maxc + MAX_N - 1) / MAX_N;
+  const int N = ((maxc + nsplit - 1) / nsplit + 15) / 16 * 16;
+  int nchunks = 0;
+  for (int g = 0; g < ngroups; ++g)
+    for (int cb = 0; cb < couts[g]; cb += N, ++nchunks) {
+      const int cnt = (couts[g] - cb) < N ? (couts[g] - cb) : N;
+      if ((cnt % 32) != 0 && (coffs[g] + cb + cnt != y_cstride)) return false;
+      if ((coffs[g] + cb) % 4) return false;
+    }
+  return nchunks <= MAX_CHUNKS;
+}
+
 int tc_conv_plan(TcConvPlan* plan, int B, int H, int W, int Cin, int Cout, int size, int stride,
                  int padding, int relu, bool has_affine, int y_cstride, int y_coff,
-                 const float* x_dev, float* y_dev) {
+                 const float* x_dev, float* y_dev, const TcPool* pool) {
   plan->enabled = false;
-  // shapes this path takes: stride-1 SAME, 1x1 or 3x3, Cin a multiple of 16, 16B-aligned stores
-  if (stride != 1 || padding != SQDET_PAD_SAME || (size != 1 && size != 3)) return 0;
-  if (Cin % 16 != 0 || Cin < 16 || (y_cstride % 4) || (y_coff % 4) || (Cout % 4)) return 0;
+  if (!tc_conv_eligible(Cin, Cout, size, stride, padding, y_cstride, y_coff)) return 0;
   TcImpl* im = new TcImpl();
   std::vector<ConvGroup> groups = {{size, Cout, y_coff, 0}};
-  int rc = plan_common(im, B, H, W, Cin, groups, relu, has_affine, y_cstride, x_dev, y_dev);
+  int rc = plan_common(im, B, H, W, Cin, groups, relu, has_affine, y_cstride, x_dev, y_dev, pool);
   if (rc <= 0) {
     void* p = im;
     release_impl(&p);
@@ -935,12 +1025,12 @@ int tc_conv_plan(TcConvPlan* plan, int B, int H, int W, int Cin, int Cout, int s
 }
 
 int tc_fire_plan(TcFirePlan* plan, int B, int H, int W, int S, int E1, int E3, const float* q_dev,
-                 float* y_dev) {
+                 float* y_dev, const TcPool* pool) {
   plan->enabled = false;
   if (S % 16 != 0 || S < 16 || (E1 % 4) || (E3 % 4)) return 0;
   TcImpl* im = new TcImpl();
   std::vector<ConvGroup> groups = {{1, E1, 0, 0}, {3, E3, E1, E1}};
-  int rc = plan_common(im, B, H, W, S, groups, 1, false, E1 + E3, q_dev, y_dev);
+  int rc = plan_common(im, B, H, W, S, groups, 1, false, E1 + E3, q_dev, y_dev, pool);
   if (rc <= 0) {
     void* p = im;
     release_impl(&p);
@@ -1006,7 +1096,7 @@ int conv2d_tc_oneshot(const float* x_dev, const float* w_hwio_dev, const float* 
                       int y_cstride, int y_coff, cudaStream_t stream) {
   TcConvPlan plan;
   int rc = tc_conv_plan(&plan, B, H, W, Cin, Cout, size, stride, padding, relu,
-                        scale_dev != nullptr, y_cstride, y_coff, x_dev, y_dev);
+                        scale_dev != nullptr, y_cstride, y_coff, x_dev, y_dev, nullptr);
   if (rc < 0) return rc;
   if (rc == 0) {
     // shape not taken by the tensor-core path (e.g. conv1, Cin = 3): same dispatch as the engine

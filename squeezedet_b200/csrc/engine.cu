@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -42,6 +43,7 @@ struct Tensor {
   int B = 0, H = 0, W = 0, C = 0;
   float* dev = nullptr;         // owned (except tensor 0 when the caller feeds its own)
   bool external = false;
+  bool materialized = true;     // false: produced and consumed inside a fused kernel only
   int64_t numel() const { return (int64_t)B * H * W * C; }
 };
 
@@ -79,6 +81,9 @@ struct Op {
   int64_t flops = 0, params = 0, min_bytes = 0;
   int launches = 0;
   TcFirePlan tcfire;             // fused expand pair (valid when tcfire.enabled)
+  bool skip = false;             // pool op whose work happens in the producer's epilogue
+  int fused_pool_op = -1;        // index of the pool op fused into this conv / fire
+  int out = -1;                  // tensor actually written (dst, or the fused pool's dst)
 };
 
 }  // namespace sqdet
@@ -221,6 +226,7 @@ static int run_conv(sqdet_engine* e, const ConvSpec& c, const float* x_override,
 }
 
 static int run_op(sqdet_engine* e, const Op& op, const float* x_override, cudaStream_t stream) {
+  if (op.skip) return SQDET_OK;
   switch (op.kind) {
     case OP_CONV:
       return run_conv(e, op.convs[0], x_override, stream);
@@ -229,7 +235,7 @@ static int run_op(sqdet_engine* e, const Op& op, const float* x_override, cudaSt
       if (rc) return rc;
       if (op.tcfire.enabled)
         return launch_fire_expand_tc(op.tcfire, e->tensors[op.convs[1].src].dev,
-                                     e->tensors[op.dst].dev, stream);
+                                     e->tensors[op.out].dev, stream);
       rc = run_conv(e, op.convs[1], nullptr, stream);
       if (rc) return rc;
       return run_conv(e, op.convs[2], nullptr, stream);
@@ -600,9 +606,56 @@ int sqdet_finalize(sqdet_engine* e) {
     return fail(SQDET_ERR_INVALID_ARG, "max_dets smaller than TOP_N_DETECTION");
   if (topn && c.top_n_detection > 1024)
     return fail(SQDET_ERR_UNSUPPORTED, "TOP_N_DETECTION above 1024 is not supported");
+  // Pool fusion: a stride-2 max-pool whose input is produced by a tensor-core conv / fire and
+  // read by nobody else runs inside that producer's epilogue; the un-pooled tensor is never
+  // materialised (for SqueezeDet: fire3+pool3, fire5+pool5).
+  for (auto& op : e->ops) op.out = op.dst;
+  {
+    static int env_fuse = -1;
+    if (env_fuse < 0) {
+      const char* a = getenv("SQDET_FUSE_POOL");
+      env_fuse = a ? atoi(a) : 1;
+    }
+    const int nops = (int)e->ops.size();
+    for (int i = 0; env_fuse && c.math_mode == SQDET_MATH_TF32X3_TC && i + 1 < nops; ++i) {
+      Op& prod = e->ops[i];
+      Op& pool = e->ops[i + 1];
+      if (pool.kind != OP_POOL || pool.src != prod.dst) continue;
+      if (prod.kind != OP_CONV && prod.kind != OP_FIRE) continue;
+      if (prod.dst == e->preds) continue;
+      int readers = 0;
+      for (const auto& o : e->ops) {
+        if (o.src == prod.dst || o.src2 == prod.dst) ++readers;
+        for (const auto& cs : o.convs)
+          if (&o != &prod && cs.src == prod.dst) ++readers;
+      }
+      if (readers != 1) continue;
+      const Tensor& pt = e->tensors[prod.dst];
+      bool ok = false;
+      if (prod.kind == OP_CONV) {
+        const ConvSpec& cs = prod.convs[0];
+        int couts[1] = {cs.Cout}, coffs[1] = {0};
+        ok = tc_conv_eligible(cs.Cin, cs.Cout, cs.size, cs.stride, cs.padding, pt.C, 0) &&
+             tc_pool_fusable(couts, coffs, 1, pt.C, pool.size, pool.stride);
+      } else {
+        const ConvSpec& sq = prod.convs[0];
+        int couts[2] = {prod.convs[1].Cout, prod.convs[2].Cout};
+        int coffs[2] = {0, prod.convs[1].Cout};
+        ok = tc_conv_eligible(sq.Cout, couts[0], 1, 1, SQDET_PAD_SAME, pt.C, 0) &&
+             tc_conv_eligible(sq.Cout, couts[1], 3, 1, SQDET_PAD_SAME, pt.C, coffs[1]) &&
+             tc_pool_fusable(couts, coffs, 2, pt.C, pool.size, pool.stride);
+      }
+      if (!ok) continue;
+      prod.fused_pool_op = i + 1;
+      prod.out = pool.dst;
+      pool.skip = true;
+      e->tensors[prod.dst].materialized = false;
+    }
+  }
   // activations
   for (size_t i = 0; i < e->tensors.size(); ++i) {
     Tensor& t = e->tensors[i];
+    if (!t.materialized) continue;
     SQ_CUDA(cudaMalloc(&t.dev, sizeof(float) * (size_t)t.numel()));
   }
   e->d_input = e->tensors[0].dev;
@@ -630,32 +683,51 @@ int sqdet_finalize(sqdet_engine* e) {
     op.launches = 0;
     if (op.kind == OP_CONV || op.kind == OP_FIRE) {
       bytes += 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.dst].numel() + 4 * op.params;
+      TcPool pool_spec;
+      const TcPool* pool_ptr = nullptr;
+      if (op.fused_pool_op >= 0) {
+        const Op& po = e->ops[op.fused_pool_op];
+        const Tensor& un = e->tensors[op.dst];
+        const Geom gh = tf_geometry(un.H, po.size, po.stride, po.padding);
+        const Geom gw = tf_geometry(un.W, po.size, po.stride, po.padding);
+        pool_spec.size = po.size;
+        pool_spec.pad_t = gh.pad_before;
+        pool_spec.pad_l = gw.pad_before;
+        pool_spec.Hp = gh.out;
+        pool_spec.Wp = gw.out;
+        pool_ptr = &pool_spec;
+        bytes = 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.out].numel() + 4 * op.params;
+      }
       if (c.math_mode == SQDET_MATH_TF32X3_TC) {
         if (op.kind == OP_CONV) {
           ConvSpec& cs = op.convs[0];
           int rc = tc_conv_plan(&cs.tc, e->tensors[cs.src].B, e->tensors[cs.src].H,
                                 e->tensors[cs.src].W, cs.Cin, cs.Cout, cs.size, cs.stride,
-                                cs.padding, cs.relu, cs.p_gamma >= 0, e->tensors[cs.dst].C,
-                                cs.y_coff, e->tensors[cs.src].dev, e->tensors[cs.dst].dev);
+                                cs.padding, cs.relu, cs.p_gamma >= 0, e->tensors[op.out].C,
+                                cs.y_coff, e->tensors[cs.src].dev, e->tensors[op.out].dev, pool_ptr);
           if (rc < 0) return rc;
+          if (pool_ptr && rc == 0)
+            return fail(SQDET_ERR_STATE, "pool fusion was promised but the conv plan declined");
         } else {
           ConvSpec& sq = op.convs[0];
           int rc = tc_conv_plan(&sq.tc, e->tensors[sq.src].B, e->tensors[sq.src].H,
                                 e->tensors[sq.src].W, sq.Cin, sq.Cout, 1, 1, SQDET_PAD_SAME, 1,
                                 false, e->tensors[sq.dst].C, 0, e->tensors[sq.src].dev,
-                                e->tensors[sq.dst].dev);
+                                e->tensors[sq.dst].dev, nullptr);
           if (rc < 0) return rc;
           const Tensor& q = e->tensors[sq.dst];
           rc = tc_fire_plan(&op.tcfire, q.B, q.H, q.W, q.C, op.convs[1].Cout, op.convs[2].Cout,
-                            q.dev, e->tensors[op.dst].dev);
+                            q.dev, e->tensors[op.out].dev, pool_ptr);
           if (rc < 0) return rc;
+          if (pool_ptr && rc == 0)
+            return fail(SQDET_ERR_STATE, "pool fusion was promised but the fire plan declined");
         }
       }
       if (op.kind == OP_CONV) op.launches = 1;
       else op.launches = 1 + (op.tcfire.enabled ? 1 : 2);
     } else if (op.kind == OP_POOL) {
-      bytes = 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.dst].numel();
-      op.launches = 1;
+      bytes = op.skip ? 0 : 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.dst].numel();
+      op.launches = op.skip ? 0 : 1;
     } else {
       bytes = 4 * 3 * e->tensors[op.dst].numel();
       op.launches = 1;
@@ -723,6 +795,8 @@ int sqdet_read_tensor(sqdet_engine* e, int id, float* host_out) {
   DeviceGuard guard(e->device);
   SQ_CUDA(cudaDeviceSynchronize());
   const Tensor& t = e->tensors[id];
+  if (!t.materialized)
+    return fail(SQDET_ERR_NOT_FOUND, "tensor '" + t.name + "' is not materialised (fused into its consumer)");
   SQ_CUDA(cudaMemcpy(host_out, t.dev, sizeof(float) * (size_t)t.numel(), cudaMemcpyDeviceToHost));
   return SQDET_OK;
 }

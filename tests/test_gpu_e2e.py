@@ -69,7 +69,11 @@ def test_layerwise_parity_small_image(net, width, height, math_mode, gpu_device)
   checked = 0
   for name, want in keep64.items():
     if name in model._tensors:
-      got = model.read_tensor(name)
+      try:
+        got = model.read_tensor(name)
+      except _lib.SqdetError as exc:
+        assert exc.code == -5, exc          # fused away (e.g. fire3 when pool3 is fused)
+        continue
       assert got.shape == want.shape, name
       # (1) the bar: within 1e-4 (relative to the tensor's scale) of the fp32 reference
       assert rel_err(got, keep32[name]) < TOL, (name, rel_err(got, keep32[name]))
