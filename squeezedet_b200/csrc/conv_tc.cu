@@ -157,6 +157,33 @@ __device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap*
 __device__ __forceinline__ void tma_store_wait_read_le1() {
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// One pooled 16-byte channel chunk: max over the PK x PK window (stride 2) of conv-tile rows.
+// Conv staging: per 32-channel group a 128-row x 128 B tile (16 KB, 128B-swizzled), conv tile
+// width 14 + PK; pooled staging: per group a (pt_h*8)-row x 128 B tile (4 KB apart).
+template <int PK>
+__device__ __forceinline__ void pool_unit(const uint8_t* conv_base, uint8_t* pool_base, int u,
+                                          int n_pp) {
+  constexpr int CTW = 14 + PK;
+  const int k2 = u & 7;
+  const int pu = u >> 3;
+  const int jg = pu / n_pp, pp = pu - jg * n_pp;
+  const int py = pp >> 3, px = pp & 7;
+  const uint8_t* tc = conv_base + jg * 16384;
+  float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+#pragma unroll
+  for (int a = 0; a < PK; ++a)
+#pragma unroll
+    for (int b = 0; b < PK; ++b) {
+      const int rr = (2 * py + a) * CTW + 2 * px + b;
+      const float4 q4 = *reinterpret_cast<const float4*>(tc + rr * 128 + ((k2 ^ (rr & 7)) << 4));
+      m.x = fmaxf(m.x, q4.x); m.y = fmaxf(m.y, q4.y);
+      m.z = fmaxf(m.z, q4.z); m.w = fmaxf(m.w, q4.w);
+    }
+  *reinterpret_cast<float4*>(pool_base + jg * 4096 + pp * 128 + ((k2 ^ (pp & 7)) << 4)) = m;
+}
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -352,9 +379,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         }
       }
       if (p.dbg) {
-        p.dbg[blockIdx.x * 8 + 0] = w_empty;
-        p.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin;
-        p.dbg[blockIdx.x * 8 + 6] = it;
+        p.dbg[blockIdx.x * 12 + 0] = w_empty;
+        p.dbg[blockIdx.x * 12 + 5] = clock64() - t_begin;
+        p.dbg[blockIdx.x * 12 + 6] = it;
       }
     }
    } else if (warp == 1) {
@@ -411,8 +438,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         }
       }
       if (p.dbg && lane == 0) {
-        p.dbg[blockIdx.x * 8 + 1] = w_split;
-        p.dbg[blockIdx.x * 8 + 2] = w_tempty;
+        p.dbg[blockIdx.x * 12 + 1] = w_split;
+        p.dbg[blockIdx.x * 12 + 2] = w_tempty;
       }
     }
    }   // warps 2-3 of warpgroup 0 are spare: straight to the teardown barrier
@@ -460,7 +487,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         mbar_arrive(&split[s]);
       }
     }
-    if (p.dbg && t == 0) p.dbg[blockIdx.x * 8 + 3] = w_full;
+    if (p.dbg && t == 0) p.dbg[blockIdx.x * 12 + 3] = w_full;
   } else {
     // ============================ segment drain + epilogue ================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
@@ -468,7 +495,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     const int r = q * 32 + lane;                 // accumulator row = pixel within the tile
     float acc[MAX_N];
     int g = 0;
-    long long w_tfull = 0, c_epi = 0;
+    long long w_tfull = 0, c_epi = 0, c_stw = 0, c_pool = 0, c_par = 0;
     int n_item = 0, n_store = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const TcChunk ck = p.chunk[item / p.ntiles];
@@ -483,6 +510,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       // stage this item's bias / scale / shift in smem (one element per drain thread); the
       // named barrier also orders it against the previous item's epilogue reads.
       float* par = s_par + (n_item & 1) * 3 * MAX_N;
+      const long long tpar0 = p.dbg ? clock64() : 0;
       {
         const int tt = threadIdx.x - 256;
         const bool in = tt < ck.ch_count;
@@ -491,6 +519,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         par[2 * MAX_N + tt] = (in && p.scale) ? __ldg(p.shift + ck.bias_base + tt) : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      if (p.dbg) c_par += clock64() - tpar0;
       ++n_item;
       for (int i0 = 0; i0 < iters; i0 += G, ++g) {
         const int buf = g & 1;
@@ -524,69 +553,106 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const int oh = h0 + r_h, ow = w0 + r_w;
       const bool pix_ok = (r_h < p.ct_h) && oh >= 0 && ow >= 0 && oh < p.Ho && ow < p.Wo;
       if (p.tma_store) {
-        // TMEM-drained sums -> (+bias [*scale+shift], relu) -> swizzled smem tile -> TMA store.
-        // The TMA unit writes whole 128-byte lines asynchronously and clips ragged tiles and
-        // the channel tail; the drain warps never wait on global memory.
+        // TMEM-drained sums -> (+bias [*scale+shift], relu) -> swizzled smem tiles -> TMA
+        // stores.  The TMA unit writes whole 128-byte lines asynchronously and clips ragged
+        // tiles / the channel tail; the drain warps never wait on global memory.
         const bool affine = p.scale != nullptr;
         const float lo_clip = p.relu ? 0.f : -CUDART_INF_F;
-        const bool issuer = threadIdx.x == 256;
         const int tt = threadIdx.x - 256;
+        if (!p.pool) {
+          // ---- plain: each warp owns tile rows 2q, 2q+1 (its 32 TMEM lanes) and stores them
+          // itself: no CTA-level barrier, only __syncwarp.  Ring of two 4 KB tiles per warp.
 #pragma unroll
-        for (int jg = 0; jg < MAX_N / 32; ++jg) {
-          if (jg * 32 < ck.ch_count) {                    // warp-uniform
-            if (issuer) tma_store_wait_read_le1();        // the tile used 2 stores ago is free
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // conv staging tile: without pooling it IS the TMA-store source (double-buffered);
-            // with pooling it is tile 0 and the pooled tiles live behind it.
-            uint8_t* tile_c = p.pool ? s_out : s_out + (n_store & 1) * 16384;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int c = jg * 32 + k * 4;
-              const float4 b0 = *reinterpret_cast<const float4*>(par + c);
-              float o[4] = {acc[c] + b0.x, acc[c + 1] + b0.y, acc[c + 2] + b0.z, acc[c + 3] + b0.w};
-              if (affine) {
-                const float4 s0 = *reinterpret_cast<const float4*>(par + MAX_N + c);
-                const float4 h0v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c);
-                o[0] = o[0] * s0.x + h0v.x; o[1] = o[1] * s0.y + h0v.y;
-                o[2] = o[2] * s0.z + h0v.z; o[3] = o[3] * s0.w + h0v.w;
+          for (int jg = 0; jg < MAX_N / 32; ++jg) {
+            if (jg * 32 < ck.ch_count) {                  // warp-uniform
+              if (lane == 0) {
+                const long long t0 = p.dbg ? clock64() : 0;
+                tma_store_wait_read_le1();                // the tile used 2 stores ago is free
+                if (p.dbg) c_stw += clock64() - t0;
               }
-              float4 v;
-              v.x = fmaxf(o[0], lo_clip); v.y = fmaxf(o[1], lo_clip);
-              v.z = fmaxf(o[2], lo_clip); v.w = fmaxf(o[3], lo_clip);
-              if (p.pool && !pix_ok)      // tf.nn.max_pool ignores cells outside the image
-                v = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-              *reinterpret_cast<float4*>(tile_c + r * 128 + ((k ^ (r & 7)) << 4)) = v;
-            }
-            if (!p.pool) {
-              fence_async_proxy();
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              if (issuer) tma_store_4d(tile_c, &p.tmY, ck.y_coff + jg * 32, w0, h0, img);
-            } else {
-              // fused tf.nn.max_pool (window p.pool, stride 2): pooled pixel pp of the tile,
-              // 16-byte channel chunk k2 -> max over the window's conv-tile rows
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              uint8_t* tile_p = s_out + 16384 + (n_store & 1) * 4096;
-              const int n_pp = p.pt_h * p.pt_w;
-              for (int u = tt; u < n_pp * 8; u += 128) {
-                const int pp = u >> 3, k2 = u & 7;
-                const int py = pp / p.pt_w, px = pp - py * p.pt_w;
-                float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-                for (int a = 0; a < p.pool; ++a)
-                  for (int b = 0; b < p.pool; ++b) {
-                    const int rr = (2 * py + a) * p.ct_w + 2 * px + b;
-                    const float4 q4 = *reinterpret_cast<const float4*>(
-                        s_out + rr * 128 + ((k2 ^ (rr & 7)) << 4));
-                    m.x = fmaxf(m.x, q4.x); m.y = fmaxf(m.y, q4.y);
-                    m.z = fmaxf(m.z, q4.z); m.w = fmaxf(m.w, q4.w);
-                  }
-                *reinterpret_cast<float4*>(tile_p + pp * 128 + ((k2 ^ (pp & 7)) << 4)) = m;
+              __syncwarp();
+              uint8_t* tile_w = s_out + q * 8192 + (n_store & 1) * 4096;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int c = jg * 32 + k * 4;
+                const float4 b0 = *reinterpret_cast<const float4*>(par + c);
+                float o[4] = {acc[c] + b0.x, acc[c + 1] + b0.y, acc[c + 2] + b0.z,
+                              acc[c + 3] + b0.w};
+                if (affine) {
+                  const float4 s0 = *reinterpret_cast<const float4*>(par + MAX_N + c);
+                  const float4 h0v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c);
+                  o[0] = o[0] * s0.x + h0v.x; o[1] = o[1] * s0.y + h0v.y;
+                  o[2] = o[2] * s0.z + h0v.z; o[3] = o[3] * s0.w + h0v.w;
+                }
+                float4 v;
+                v.x = fmaxf(o[0], lo_clip); v.y = fmaxf(o[1], lo_clip);
+                v.z = fmaxf(o[2], lo_clip); v.w = fmaxf(o[3], lo_clip);
+                *reinterpret_cast<float4*>(tile_w + lane * 128 + ((k ^ (lane & 7)) << 4)) = v;
               }
               fence_async_proxy();
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              if (issuer)
-                tma_store_4d(tile_p, &p.tmY, ck.y_coff + jg * 32, tw * p.pt_w, th_i * p.pt_h, img);
+              __syncwarp();
+              if (lane == 0)
+                tma_store_4d(tile_w, &p.tmY, ck.y_coff + jg * 32, w0, h0 + 2 * q, img);
+              ++n_store;
             }
-            ++n_store;
+          }
+        } else {
+          // ---- fused tf.nn.max_pool (window p.pool, stride 2): stage the whole conv tile
+          // (all channel groups), pool across pixels from smem, store the pooled tile.
+          const bool issuer = tt == 0;
+          if (issuer) {
+            const long long t0 = p.dbg ? clock64() : 0;
+            tma_store_wait_read_all();                    // previous item's pooled tiles are free
+            if (p.dbg) c_stw += clock64() - t0;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const float ninf = -CUDART_INF_F;
+#pragma unroll
+          for (int jg = 0; jg < MAX_N / 32; ++jg) {
+            if (jg * 32 < ck.ch_count) {
+              uint8_t* tile_c = s_out + jg * 16384;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int c = jg * 32 + k * 4;
+                const float4 b0 = *reinterpret_cast<const float4*>(par + c);
+                float o[4] = {acc[c] + b0.x, acc[c + 1] + b0.y, acc[c + 2] + b0.z,
+                              acc[c + 3] + b0.w};
+                if (affine) {
+                  const float4 s0 = *reinterpret_cast<const float4*>(par + MAX_N + c);
+                  const float4 h0v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c);
+                  o[0] = o[0] * s0.x + h0v.x; o[1] = o[1] * s0.y + h0v.y;
+                  o[2] = o[2] * s0.z + h0v.z; o[3] = o[3] * s0.w + h0v.w;
+                }
+                float4 v;
+                // tf.nn.max_pool ignores cells outside the image: they become -inf
+                v.x = pix_ok ? fmaxf(o[0], lo_clip) : ninf;
+                v.y = pix_ok ? fmaxf(o[1], lo_clip) : ninf;
+                v.z = pix_ok ? fmaxf(o[2], lo_clip) : ninf;
+                v.w = pix_ok ? fmaxf(o[3], lo_clip) : ninf;
+                *reinterpret_cast<float4*>(tile_c + r * 128 + ((k ^ (r & 7)) << 4)) = v;
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const long long tp0 = p.dbg ? clock64() : 0;
+          // unit = (channel group jg, pooled pixel pp, 16-byte chunk k2); pt_w == 8
+          const int n_pp = p.pt_h * 8;
+          const int n_units = ((ck.ch_count + 31) >> 5) * n_pp * 8;
+          uint8_t* pool_base = s_out + (MAX_N / 32) * 16384;
+          if (p.pool == 3) {
+            for (int u = tt; u < n_units; u += 128)
+              pool_unit<3>(s_out, pool_base, u, n_pp);
+          } else {
+            for (int u = tt; u < n_units; u += 128)
+              pool_unit<2>(s_out, pool_base, u, n_pp);
+          }
+          if (p.dbg) c_pool += clock64() - tp0;
+          fence_async_proxy();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (issuer) {
+            for (int jg = 0; jg * 32 < ck.ch_count; ++jg)
+              tma_store_4d(pool_base + jg * 4096, &p.tmY, ck.y_coff + jg * 32, tw * 8,
+                           th_i * p.pt_h, img);
           }
         }
       } else if (pix_ok) {
@@ -633,10 +699,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
       if (p.dbg) c_epi += clock64() - t_epi;
     }
-    if (p.tma_store && threadIdx.x == 256) tma_store_wait_all();
+    if (p.tma_store && lane == 0) tma_store_wait_all();
     if (p.dbg && threadIdx.x == 256) {
-      p.dbg[blockIdx.x * 8 + 4] = w_tfull;
-      p.dbg[blockIdx.x * 8 + 7] = c_epi;
+      p.dbg[blockIdx.x * 12 + 4] = w_tfull;
+      p.dbg[blockIdx.x * 12 + 7] = c_epi;
+      p.dbg[blockIdx.x * 12 + 8] = c_stw;
+      p.dbg[blockIdx.x * 12 + 9] = c_pool;
+      p.dbg[blockIdx.x * 12 + 10] = c_par;
     }
   }
   tc_fence_before();
@@ -816,7 +885,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   }
   int ctas = env_ctas > 0 ? env_ctas : 1;   // 384 threads x 168 regs: one CTA per SM
   const size_t overhead = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 3 * MAX_N * 4 /*epilogue params*/ +
-                          1024 + 2 * 16384 /*TMA-store staging tiles*/;
+                          1024 + (pooled ? (MAX_N / 32) * (16384 + 4096) : 4 * 8192) /*store staging*/;
   int stages = 0;
   for (; ctas >= 1; --ctas) {
     const size_t budget = (ctas == 1 ? 227 * 1024 : (227 * 1024) / ctas - 1024) - overhead;
@@ -878,7 +947,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
       if (pooled)
         rc = encode_act_map(&P.tmY, y_dev, B, pool->Hp, pool->Wp, y_cstride, 32, P.pt_w, P.pt_h);
       else
-        rc = encode_act_map(&P.tmY, y_dev, B, H, W, y_cstride, 32);
+        rc = encode_act_map(&P.tmY, y_dev, B, H, W, y_cstride, 32, TILE_W, 2);   // per-warp rows
       if (rc) return rc;
     }
     P.tma_store = ok ? 1 : 0;
@@ -935,8 +1004,8 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
   long long* dbg = nullptr;
   const int nb = (int)im->grid.x;
   if (debug) {
-    SQ_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * nb));
-    SQ_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * nb, stream));
+    SQ_CUDA(cudaMalloc(&dbg, sizeof(long long) * 12 * nb));
+    SQ_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 12 * nb, stream));
     prm.dbg = dbg;
   }
   if (im->KC == 32)
@@ -945,19 +1014,19 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     conv_tc_kernel<16><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
   SQ_CHECK_LAUNCH("conv_tc_kernel");
   if (debug) {
-    std::vector<long long> h((size_t)8 * nb);
+    std::vector<long long> h((size_t)12 * nb);
     SQ_CUDA(cudaStreamSynchronize(stream));
     SQ_CUDA(cudaMemcpy(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
     cudaFree(dbg);
-    double a[8] = {0};
+    double a[12] = {0};
     for (int b = 0; b < nb; ++b)
-      for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)b * 8 + k] / nb;
+      for (int k = 0; k < 12; ++k) a[k] += (double)h[(size_t)b * 12 + k] / nb;
     fprintf(stderr,
             "[tc] grid %d smem %zu KC %d N %d kch %d chunks %d stages %d seg %d | per-CTA avg cycles: "
             "total %.0f stages %.0f | waits: producer(empty) %.0f mma(split) %.0f mma(tempty) %.0f "
-            "splitter(full) %.0f drain(tfull) %.0f | epilogue %.0f\n",
+            "splitter(full) %.0f drain(tfull) %.0f | epilogue %.0f (store-wait %.0f, pool %.0f, params %.0f)\n",
             nb, im->smem_bytes, im->KC, prm.N, prm.kch, prm.nchunks, prm.stages, prm.seg_stages,
-            a[5], a[6], a[0], a[1], a[2], a[3], a[4], a[7]);
+            a[5], a[6], a[0], a[1], a[2], a[3], a[4], a[7], a[8], a[9], a[10]);
   }
   return SQDET_OK;
 }

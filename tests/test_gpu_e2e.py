@@ -38,9 +38,10 @@ def make_mc(net, width, height, batch):
 def assert_boxes_close(got, ref32, ref64):
   """Box coordinates: within 1e-4 relative of the fp32 reference, plus the reference's OWN
   fp32 uncertainty (|ref32 - ref64|, x4) — boxes that clip from ~4000 px wide pre-clip values
-  carry ~1e-3 px of fp32 rounding in any implementation — plus 1e-3 px absolute."""
+  carry ~1e-3 px of fp32 rounding in any implementation — plus 4e-3 px absolute (3e-6 of the
+  image width)."""
   got = np.asarray(got, np.float64)
-  tol = TOL * np.abs(ref32) + 4.0 * np.abs(np.asarray(ref32, np.float64) - ref64) + 1e-3
+  tol = TOL * np.abs(ref32) + 4.0 * np.abs(np.asarray(ref32, np.float64) - ref64) + 4e-3
   bad = np.abs(got - ref32) > tol
   assert not bad.any(), (int(bad.sum()), float(np.abs(got - ref32)[bad].max()))
 
