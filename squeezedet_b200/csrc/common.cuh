@@ -55,6 +55,12 @@ struct ConvArgs {
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t stream);
 
+bool conv_pool_simt_eligible(int Cin, int Cout, int ksize, int stride, int pool_size,
+                             int pool_stride);
+int launch_conv_pool_simt(const float* x, const float* w, const float* bias, const float* scale,
+                          const float* shift, float* y, int B, int H, int W, int Cout, int ksize,
+                          int conv_padding, int relu, int pool_padding, cudaStream_t stream);
+
 int launch_maxpool(const float* x, float* y, int B, int H, int W, int C, int size,
                    int stride, int padding, cudaStream_t stream);
 int launch_add_relu(const float* a, const float* b, float* y, int64_t n, cudaStream_t stream);

@@ -83,6 +83,7 @@ struct Op {
   TcFirePlan tcfire;             // fused expand pair (valid when tcfire.enabled)
   bool skip = false;             // pool op whose work happens in the producer's epilogue
   int fused_pool_op = -1;        // index of the pool op fused into this conv / fire
+  bool first_layer_fused = false;  // Cin=3 stride-2 conv + 3x3/2 pool as one FFMA kernel
   int out = -1;                  // tensor actually written (dst, or the fused pool's dst)
 };
 
@@ -229,6 +230,16 @@ static int run_op(sqdet_engine* e, const Op& op, const float* x_override, cudaSt
   if (op.skip) return SQDET_OK;
   switch (op.kind) {
     case OP_CONV:
+      if (op.first_layer_fused) {
+        const ConvSpec& c = op.convs[0];
+        const Op& po = e->ops[op.fused_pool_op];
+        const Tensor& in = e->tensors[c.src];
+        const float* x = (c.src == 0 && x_override) ? x_override : in.dev;
+        return launch_conv_pool_simt(x, e->params[c.p_kernel].dev,
+                                     c.p_bias >= 0 ? e->params[c.p_bias].dev : nullptr, c.scale,
+                                     c.shift, e->tensors[op.out].dev, in.B, in.H, in.W, c.Cout,
+                                     c.size, c.padding, c.relu, po.padding, stream);
+      }
       return run_conv(e, op.convs[0], x_override, stream);
     case OP_FIRE: {
       int rc = run_conv(e, op.convs[0], x_override, stream);
@@ -617,10 +628,31 @@ int sqdet_finalize(sqdet_engine* e) {
       env_fuse = a ? atoi(a) : 1;
     }
     const int nops = (int)e->ops.size();
+    // first layer: Cin = 3, stride-2 conv + 3x3/2 pool -> one FFMA kernel (both math modes)
+    for (int i = 0; env_fuse && i + 1 < nops; ++i) {
+      Op& prod = e->ops[i];
+      Op& pool = e->ops[i + 1];
+      if (prod.kind != OP_CONV || pool.kind != OP_POOL || pool.src != prod.dst) continue;
+      const ConvSpec& cs = prod.convs[0];
+      if (!conv_pool_simt_eligible(cs.Cin, cs.Cout, cs.size, cs.stride, pool.size, pool.stride))
+        continue;
+      int readers = 0;
+      for (const auto& o : e->ops) {
+        if (o.src == prod.dst || o.src2 == prod.dst) ++readers;
+        for (const auto& c2 : o.convs)
+          if (&o != &prod && c2.src == prod.dst) ++readers;
+      }
+      if (readers != 1 || prod.dst == e->preds) continue;
+      prod.first_layer_fused = true;
+      prod.fused_pool_op = i + 1;
+      prod.out = pool.dst;
+      pool.skip = true;
+      e->tensors[prod.dst].materialized = false;
+    }
     for (int i = 0; env_fuse && c.math_mode == SQDET_MATH_TF32X3_TC && i + 1 < nops; ++i) {
       Op& prod = e->ops[i];
       Op& pool = e->ops[i + 1];
-      if (pool.kind != OP_POOL || pool.src != prod.dst) continue;
+      if (pool.kind != OP_POOL || pool.src != prod.dst || pool.skip) continue;
       if (prod.kind != OP_CONV && prod.kind != OP_FIRE) continue;
       if (prod.dst == e->preds) continue;
       int readers = 0;
@@ -685,7 +717,9 @@ int sqdet_finalize(sqdet_engine* e) {
       bytes += 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.dst].numel() + 4 * op.params;
       TcPool pool_spec;
       const TcPool* pool_ptr = nullptr;
-      if (op.fused_pool_op >= 0) {
+      if (op.first_layer_fused) {
+        bytes = 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.out].numel() + 4 * op.params;
+      } else if (op.fused_pool_op >= 0) {
         const Op& po = e->ops[op.fused_pool_op];
         const Tensor& un = e->tensors[op.dst];
         const Geom gh = tf_geometry(un.H, po.size, po.stride, po.padding);
@@ -698,7 +732,7 @@ int sqdet_finalize(sqdet_engine* e) {
         pool_ptr = &pool_spec;
         bytes = 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.out].numel() + 4 * op.params;
       }
-      if (c.math_mode == SQDET_MATH_TF32X3_TC) {
+      if (c.math_mode == SQDET_MATH_TF32X3_TC && !op.first_layer_fused) {
         if (op.kind == OP_CONV) {
           ConvSpec& cs = op.convs[0];
           int rc = tc_conv_plan(&cs.tc, e->tensors[cs.src].B, e->tensors[cs.src].H,
