@@ -45,8 +45,8 @@ struct ConvPoolParams {
   int tiles_w, tiles_h;
 };
 
-template <int KS>
-__global__ void __launch_bounds__(384)
+template <int KS, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 conv_pool_simt_kernel(const ConvPoolParams p) {
   constexpr int PH = 2 * (CT_H - 1) + KS;          // input patch rows
   constexpr int PW = 2 * (CT_W - 1) + KS;          // input patch cols (pixels)
@@ -72,13 +72,17 @@ conv_pool_simt_kernel(const ConvPoolParams p) {
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
   {
     const float* xin = p.x + (size_t)img * p.H * p.W * 3;
-    for (int i = tid; i < PH * PW * 3; i += nthreads) {
-      const int row = i / (PW * 3), col = i - row * (PW * 3);
-      const int iy = iy0 + row, ixc = ix0 * 3 + col;      // col counts floats (pixel*3 + c)
-      float v = 0.f;
-      if (iy >= 0 && iy < p.H && ixc >= 0 && ixc < p.W * 3)
-        v = __ldg(xin + (size_t)iy * p.W * 3 + ixc);
-      s_patch[i] = v;
+    const int wid = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+    for (int row = wid; row < PH; row += nwarps) {       // one warp per patch row: coalesced
+      const int iy = iy0 + row;
+      const bool row_ok = iy >= 0 && iy < p.H;
+      const float* src = xin + (size_t)iy * p.W * 3 + ix0 * 3;
+      for (int col = lane; col < PW * 3; col += 32) {    // col counts floats (pixel*3 + c)
+        const int ixc = ix0 * 3 + col;
+        float v = 0.f;
+        if (row_ok && ixc >= 0 && ixc < p.W * 3) v = __ldg(src + col);
+        s_patch[row * (PW * 3) + col] = v;
+      }
     }
   }
   __syncthreads();
@@ -213,26 +217,23 @@ int launch_conv_pool_simt(const float* x, const float* w, const float* bias, con
   p.tiles_w = (p.Wp + PT_W - 1) / PT_W;
   const unsigned grid = (unsigned)(B * p.tiles_h * p.tiles_w);
   const int threads = 64 * (Cout / 16);
-  if (ksize == 3) {
-    const size_t smem = smem_bytes_for<3>(Cout);
-    static bool set3 = false;
-    if (!set3) {
-      SQ_CUDA(cudaFuncSetAttribute(conv_pool_simt_kernel<3>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-      set3 = true;
-    }
-    conv_pool_simt_kernel<3><<<grid, threads, smem, stream>>>(p);
-  } else {
-    const size_t smem = smem_bytes_for<7>(Cout);
-    if (smem > 232448) return fail(SQDET_ERR_UNSUPPORTED, "conv+pool: tile does not fit in smem");
-    static bool set7 = false;
-    if (!set7) {
-      SQ_CUDA(cudaFuncSetAttribute(conv_pool_simt_kernel<7>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-      set7 = true;
-    }
-    conv_pool_simt_kernel<7><<<grid, threads, smem, stream>>>(p);
-  }
+  const size_t smem = ksize == 3 ? smem_bytes_for<3>(Cout) : smem_bytes_for<7>(Cout);
+  if (smem > 232448) return fail(SQDET_ERR_UNSUPPORTED, "conv+pool: tile does not fit in smem");
+#define SQ_LAUNCH_CP(KS_, NT_, MINB_)                                                          \
+  do {                                                                                         \
+    static bool attr_set = false;                                                              \
+    if (!attr_set) {                                                                           \
+      SQ_CUDA(cudaFuncSetAttribute(conv_pool_simt_kernel<KS_, NT_, MINB_>,                     \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));      \
+      attr_set = true;                                                                         \
+    }                                                                                          \
+    conv_pool_simt_kernel<KS_, NT_, MINB_><<<grid, NT_, smem, stream>>>(p);                    \
+  } while (0)
+  if (ksize == 3 && threads <= 256) SQ_LAUNCH_CP(3, 256, 2);
+  else if (ksize == 3) SQ_LAUNCH_CP(3, 384, 1);
+  else if (threads <= 256) SQ_LAUNCH_CP(7, 256, 1);
+  else SQ_LAUNCH_CP(7, 384, 1);
+#undef SQ_LAUNCH_CP
   SQ_CHECK_LAUNCH("conv_pool_simt_kernel");
   return SQDET_OK;
 }
