@@ -151,6 +151,21 @@ int sqdet_results_dev(sqdet_engine* e, float** det_boxes, float** det_probs,
 int sqdet_detect(sqdet_engine* e, const float* images, float* det_boxes,
                  float* det_probs, int64_t* det_class, sqdet_det* dets,
                  int32_t* counts, void* stream);
+/* Pipelined host-buffer path (depth 2): sqdet_submit enqueues H2D (own copy stream) ->
+ * [uint8 -> fp32 - mc.BGR_MEANS on the GPU] -> forward -> D2H of the filtered records and
+ * returns at once; sqdet_wait blocks until the OLDEST outstanding submit has delivered into its
+ * dets/counts buffers.  With two submits in flight the copy of batch i+1 overlaps the compute
+ * of batch i.  img_type SQDET_IMG_F32: [B,H,W,3] fp32 BGR, mean-subtracted (feed_dict
+ * semantics, src/demo.py:190-195); SQDET_IMG_U8: [B,H,W,3] uint8 BGR exactly as cv2.imread /
+ * cv2.resize leave it (src/demo.py:187-189) - the engine applies `im - mc.BGR_MEANS`
+ * (src/demo.py:190, src/dataset/imdb.py:88).  Host buffers must stay valid (and should be
+ * pinned) until the matching sqdet_wait.  SQDET_ERR_STATE if two submits are already pending. */
+#define SQDET_IMG_F32 0
+#define SQDET_IMG_U8  1
+int sqdet_set_bgr_means(sqdet_engine* e, const double bgr_means[3]);   /* mc.BGR_MEANS */
+int sqdet_submit(sqdet_engine* e, const void* images, int img_type, sqdet_det* dets,
+                 int32_t* counts);
+int sqdet_wait(sqdet_engine* e);
 /* Kernel launches issued by one sqdet_forward (for accounting).                        */
 int sqdet_launches_per_forward(sqdet_engine* e);
 

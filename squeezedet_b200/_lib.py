@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libsqdet_b200.so')
 OK = 0
 PAD_SAME, PAD_VALID = 0, 1
 MATH_FP32_SIMT, MATH_TF32X3_TC = 0, 1
+IMG_F32, IMG_U8 = 0, 1
 _PAD = {'SAME': PAD_SAME, 'VALID': PAD_VALID}
 
 
@@ -77,6 +78,9 @@ SIGNATURES = {
     'sqdet_results_dev': (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                                C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int32)]),
     'sqdet_detect': (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
+    'sqdet_set_bgr_means': (_i, [_vp, _vp]),
+    'sqdet_submit': (_i, [_vp, _vp, _i, _vp, _vp]),
+    'sqdet_wait': (_i, [_vp]),
     'sqdet_launches_per_forward': (_i, [_vp]),
     'sqdet_conv2d': (_i, [_fp, _fp, _fp, _fp, _fp, _fp] + [_i] * 12 + [_vp]),
     'sqdet_maxpool_nhwc': (_i, [_fp, _fp] + [_i] * 7 + [_vp]),

@@ -112,11 +112,24 @@ struct sqdet_engine {
   int32_t* d_counts = nullptr;
   int max_dets = 0;
   float* d_input = nullptr;       // engine-owned input buffer (host-path + graph)
-  // CUDA graph of one forward, keyed by (input pointer, stream)
-  cudaGraphExec_t graph_exec = nullptr;
-  const float* graph_input = nullptr;
-  cudaStream_t graph_stream = nullptr;
+  // CUDA graphs of one forward, keyed by (input pointer, stream); small LRU-less cache
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    const float* input = nullptr;
+    cudaStream_t stream = nullptr;
+  };
+  GraphEntry graphs[4];
+  int graph_next = 0;
   bool use_graph = true;
+  // pipelined host path (sqdet_submit / sqdet_wait), depth 2
+  cudaStream_t copy_stream = nullptr;
+  float* d_in_slot[2] = {nullptr, nullptr};       // slot 0 aliases tensors[0].dev
+  uint8_t* d_u8_slot[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  bool slot_used[2] = {false, false};
+  long long n_submitted = 0, n_waited = 0;
+  double bgr_means[3] = {103.939, 116.779, 123.68};   // config.py:72
   cudaStream_t own_stream = nullptr;
   std::vector<cudaEvent_t> prof_events;
 };
@@ -335,12 +348,10 @@ static int prepare_params(sqdet_engine* e) {
 }
 
 static void drop_graph(sqdet_engine* e) {
-  if (e->graph_exec) {
-    cudaGraphExecDestroy(e->graph_exec);
-    e->graph_exec = nullptr;
+  for (auto& g : e->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = sqdet_engine::GraphEntry();
   }
-  e->graph_input = nullptr;
-  e->graph_stream = nullptr;
 }
 
 static int enqueue_all(sqdet_engine* e, const float* images_dev, cudaStream_t stream) {
@@ -361,8 +372,14 @@ static int forward_impl(sqdet_engine* e, const float* images_dev, cudaStream_t s
   if (rc) return rc;
   const bool can_graph = e->use_graph && stream != nullptr;   // legacy stream cannot capture
   if (!can_graph) return enqueue_all(e, images_dev, stream);
-  if (!e->graph_exec || e->graph_input != images_dev || e->graph_stream != stream) {
-    drop_graph(e);
+  sqdet_engine::GraphEntry* hit = nullptr;
+  for (auto& g : e->graphs)
+    if (g.exec && g.input == images_dev && g.stream == stream) hit = &g;
+  if (!hit) {
+    sqdet_engine::GraphEntry& slot = e->graphs[e->graph_next];
+    e->graph_next = (e->graph_next + 1) % 4;
+    if (slot.exec) cudaGraphExecDestroy(slot.exec);
+    slot = sqdet_engine::GraphEntry();
     cudaGraph_t graph = nullptr;
     SQ_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
     rc = enqueue_all(e, images_dev, stream);
@@ -372,13 +389,14 @@ static int forward_impl(sqdet_engine* e, const float* images_dev, cudaStream_t s
       return rc;
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
-    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    ce = cudaGraphInstantiate(&slot.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
-    e->graph_input = images_dev;
-    e->graph_stream = stream;
+    slot.input = images_dev;
+    slot.stream = stream;
+    hit = &slot;
   }
-  SQ_CUDA(cudaGraphLaunch(e->graph_exec, stream));
+  SQ_CUDA(cudaGraphLaunch(hit->exec, stream));
   return SQDET_OK;
 }
 
@@ -449,6 +467,13 @@ int sqdet_destroy(sqdet_engine* e) {
   cudaFree(e->d_cls);
   cudaFree(e->d_dets);   // also owns d_counts (one blob); d_input aliases tensors[0].dev
   for (auto ev : e->prof_events) cudaEventDestroy(ev);
+  for (int k = 0; k < 2; ++k) {
+    if (k == 1 && e->d_in_slot[1]) cudaFree(e->d_in_slot[1]);
+    if (e->d_u8_slot[k]) cudaFree(e->d_u8_slot[k]);
+    if (e->ev_h2d[k]) cudaEventDestroy(e->ev_h2d[k]);
+    if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   (void)cudaGetLastError();   // never leave a stale error for the next engine's launch checks
   delete e;
@@ -947,6 +972,75 @@ int sqdet_detect(sqdet_engine* e, const float* images, float* det_boxes, float* 
     SQ_CUDA(cudaMemcpyAsync(counts, e->d_counts, sizeof(int32_t) * (size_t)c.batch_size,
                             cudaMemcpyDeviceToHost, stream));
   SQ_CUDA(cudaStreamSynchronize(stream));
+  return SQDET_OK;
+}
+
+int sqdet_set_bgr_means(sqdet_engine* e, const double bgr_means[3]) {
+  if (!e || !bgr_means) return fail(SQDET_ERR_INVALID_ARG, "sqdet_set_bgr_means: null argument");
+  for (int i = 0; i < 3; ++i) e->bgr_means[i] = bgr_means[i];
+  return SQDET_OK;
+}
+
+int sqdet_submit(sqdet_engine* e, const void* images, int img_type, sqdet_det* dets,
+                 int32_t* counts) {
+  if (!e || !images) return fail(SQDET_ERR_INVALID_ARG, "sqdet_submit: null argument");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_submit before sqdet_finalize");
+  if (img_type != SQDET_IMG_F32 && img_type != SQDET_IMG_U8)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_submit: unknown img_type");
+  if (e->n_submitted - e->n_waited >= 2)
+    return fail(SQDET_ERR_STATE, "sqdet_submit: two batches already in flight; call sqdet_wait");
+  DeviceGuard guard(e->device);
+  const sqdet_config& c = e->cfg;
+  const int slot = (int)(e->n_submitted & 1);
+  const int64_t n_pix = (int64_t)c.batch_size * c.image_height * c.image_width;
+  if (!e->copy_stream) {
+    SQ_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    e->d_in_slot[0] = e->tensors[0].dev;
+    SQ_CUDA(cudaMalloc(&e->d_in_slot[1], sizeof(float) * (size_t)n_pix * 3));
+    for (int k = 0; k < 2; ++k) {
+      SQ_CUDA(cudaEventCreateWithFlags(&e->ev_h2d[k], cudaEventDisableTiming));
+      SQ_CUDA(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
+    }
+  }
+  if (img_type == SQDET_IMG_U8 && !e->d_u8_slot[slot])
+    SQ_CUDA(cudaMalloc(&e->d_u8_slot[slot], (size_t)n_pix * 3));
+  cudaStream_t cs = e->copy_stream, ks = e->own_stream;
+  // the slot's input buffers are free once the forward that last read them has finished
+  if (e->slot_used[slot]) SQ_CUDA(cudaStreamWaitEvent(cs, e->ev_done[slot], 0));
+  if (img_type == SQDET_IMG_U8)
+    SQ_CUDA(cudaMemcpyAsync(e->d_u8_slot[slot], images, (size_t)n_pix * 3, cudaMemcpyHostToDevice, cs));
+  else
+    SQ_CUDA(cudaMemcpyAsync(e->d_in_slot[slot], images, sizeof(float) * (size_t)n_pix * 3,
+                            cudaMemcpyHostToDevice, cs));
+  SQ_CUDA(cudaEventRecord(e->ev_h2d[slot], cs));
+  SQ_CUDA(cudaStreamWaitEvent(ks, e->ev_h2d[slot], 0));
+  int rc = SQDET_OK;
+  if (img_type == SQDET_IMG_U8) {
+    rc = launch_u8_meansub(e->d_u8_slot[slot], e->d_in_slot[slot], n_pix, e->bgr_means[0],
+                           e->bgr_means[1], e->bgr_means[2], ks);
+    if (rc) return rc;
+  }
+  rc = forward_impl(e, e->d_in_slot[slot], ks);
+  if (rc) return rc;
+  if (dets)
+    SQ_CUDA(cudaMemcpyAsync(dets, e->d_dets, sizeof(sqdet_det) * (size_t)c.batch_size * e->max_dets,
+                            cudaMemcpyDeviceToHost, ks));
+  if (counts)
+    SQ_CUDA(cudaMemcpyAsync(counts, e->d_counts, sizeof(int32_t) * (size_t)c.batch_size,
+                            cudaMemcpyDeviceToHost, ks));
+  SQ_CUDA(cudaEventRecord(e->ev_done[slot], ks));
+  e->slot_used[slot] = true;
+  ++e->n_submitted;
+  return SQDET_OK;
+}
+
+int sqdet_wait(sqdet_engine* e) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  if (e->n_waited >= e->n_submitted) return fail(SQDET_ERR_STATE, "sqdet_wait: nothing in flight");
+  DeviceGuard guard(e->device);
+  const int slot = (int)(e->n_waited & 1);
+  SQ_CUDA(cudaEventSynchronize(e->ev_done[slot]));
+  ++e->n_waited;
   return SQDET_OK;
 }
 

@@ -252,6 +252,8 @@ class ModelSkeleton:
         self._engine, self.preds.id, anchors.ctypes.data, anchors.shape[0]))
     _lib.check(self._lib.sqdet_finalize(self._engine))
     self._finalized = True
+    means = np.ascontiguousarray(np.asarray(mc.BGR_MEANS, dtype=np.float64).reshape(3))
+    _lib.check(self._lib.sqdet_set_bgr_means(self._engine, means.ctypes.data))
     B, A = mc.BATCH_SIZE, anchors.shape[0]
     self.det_boxes = GraphTensor(self, 'bbox', None, (B, A, 4), 'det_boxes')
     self.det_probs = GraphTensor(self, 'score', None, (B, A), 'det_probs')
@@ -328,6 +330,32 @@ class ModelSkeleton:
     counts = np.empty((B,), np.int32)
     _lib.check(self._lib.sqdet_detect(self._engine, arr.ctypes.data, None, None, None,
                                       dets.ctypes.data, counts.ctypes.data, None))
+    return dets, counts
+
+  # pipelined host path: copy of batch i+1 overlaps the compute of batch i (depth 2)
+  def submit(self, images_ptr, dets_ptr, counts_ptr, img_type=_lib.IMG_F32):
+    """Enqueue one batch (raw host pointers, ideally pinned; must stay valid until the
+    matching wait()).  img_type: _lib.IMG_F32 (feed_dict semantics) or _lib.IMG_U8 (uint8
+    BGR as cv2 returns it; `- mc.BGR_MEANS` happens on the GPU, demo.py:187-190)."""
+    _lib.check(self._lib.sqdet_submit(self._engine, images_ptr, int(img_type), dets_ptr,
+                                      counts_ptr))
+
+  def wait(self):
+    _lib.check(self._lib.sqdet_wait(self._engine))
+
+  def detect_u8(self, images_u8):
+    """uint8 BGR images [B,H,W,3] (already at mc.IMAGE_WIDTH x IMAGE_HEIGHT) ->
+    (dets, counts): the demo.py:187-199 loop body from `im - mc.BGR_MEANS` on, on the GPU."""
+    mc = self.mc
+    arr = np.ascontiguousarray(np.asarray(images_u8, dtype=np.uint8))
+    want = (mc.BATCH_SIZE, mc.IMAGE_HEIGHT, mc.IMAGE_WIDTH, 3)
+    if arr.shape != want:
+      raise ValueError('Cannot feed value of shape %r for image_input, which has shape %r'
+                       % (arr.shape, want))
+    dets = np.empty((mc.BATCH_SIZE, self.max_dets), _lib.DET_DTYPE)
+    counts = np.empty((mc.BATCH_SIZE,), np.int32)
+    self.submit(arr.ctypes.data, dets.ctypes.data, counts.ctypes.data, _lib.IMG_U8)
+    self.wait()
     return dets, counts
 
   @staticmethod

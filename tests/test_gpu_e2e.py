@@ -191,3 +191,34 @@ def test_set_param_errors(gpu_device):
     m.set_param('conv1/kernels', np.zeros((3, 3, 3, 63), np.float32))
   with pytest.raises(_lib.SqdetError):
     m.set_param('nope/kernels', np.zeros((1,), np.float32))
+
+
+def test_pipelined_submit_and_uint8_input(gpu_device):
+  """sqdet_submit/sqdet_wait (depth-2 pipeline) and the uint8 path: same records as the
+  synchronous fp32 feed of `im - BGR_MEANS` (demo.py:187-190)."""
+  mc = make_mc('squeezeDet', 320, 96, 2)
+  m = SqueezeDet(mc, gpu_device)
+  m.load_weights(synth.synthetic_weights(synth.model_param_specs(m), seed=8))
+  rng = np.random.default_rng(3)
+  batches = [rng.integers(0, 256, (2, 96, 320, 3), dtype=np.uint8) for _ in range(4)]
+  feeds = [(b.astype(np.float32) - np.asarray(mc.BGR_MEANS)).astype(np.float32) for b in batches]
+  want = [m.detect_records(f) for f in feeds]
+  # uint8 path, synchronous convenience
+  for b, (wd, wc) in zip(batches, want):
+    d, c = m.detect_u8(b)
+    assert np.array_equal(c, wc) and np.array_equal(d, wd)
+  # pipelined, two in flight, mixing input types
+  outs = [(np.empty((2, m.max_dets), _lib.DET_DTYPE), np.empty((2,), np.int32)) for _ in batches]
+  keep_alive = []
+  for i in range(len(batches)):
+    src = np.ascontiguousarray(batches[i]) if i % 2 == 0 else np.ascontiguousarray(feeds[i])
+    keep_alive.append(src)
+    m.submit(src.ctypes.data, outs[i][0].ctypes.data, outs[i][1].ctypes.data,
+             _lib.IMG_U8 if i % 2 == 0 else _lib.IMG_F32)
+    if i >= 1:
+      m.wait()
+  m.wait()
+  for (d, c), (wd, wc) in zip(outs, want):
+    assert np.array_equal(c, wc) and np.array_equal(d, wd)
+  with pytest.raises(_lib.SqdetError):
+    m.wait()                                   # nothing in flight
