@@ -67,24 +67,36 @@ conv_pool_simt_kernel(const ConvPoolParams p) {
   const int ch0 = 2 * ph0 - p.ppad_t, cw0 = 2 * pw0 - p.ppad_l;   // conv origin
   const int iy0 = 2 * ch0 - p.cpad_t, ix0 = 2 * cw0 - p.cpad_l;   // input origin
 
-  // ---- stage weights and the input patch ----
-  for (int i = tid; i < K * p.Cout / 4; i += nthreads)
-    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+  // ---- stage weights and the input patch with cp.async (fire-and-forget, so the ~20
+  // row-segment loads per thread overlap instead of paying one L2 round trip each) ----
+  for (int i = tid; i < K * p.Cout / 4; i += nthreads) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(s_w + i * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p.w + i * 4) : "memory");
+  }
   {
     const float* xin = p.x + (size_t)img * p.H * p.W * 3;
     const int wid = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
     for (int row = wid; row < PH; row += nwarps) {       // one warp per patch row: coalesced
       const int iy = iy0 + row;
       const bool row_ok = iy >= 0 && iy < p.H;
-      const float* src = xin + (size_t)iy * p.W * 3 + ix0 * 3;
-      for (int col = lane; col < PW * 3; col += 32) {    // col counts floats (pixel*3 + c)
-        const int ixc = ix0 * 3 + col;
-        float v = 0.f;
-        if (row_ok && ixc >= 0 && ixc < p.W * 3) v = __ldg(src + col);
-        s_patch[row * (PW * 3) + col] = v;
+      const float* src = xin + (size_t)(row_ok ? iy : 0) * p.W * 3;
+#pragma unroll
+      for (int it = 0; it < (PW * 3 + 31) / 32; ++it) {  // col counts floats (pixel*3 + c)
+        const int col = lane + it * 32;
+        if (col < PW * 3) {
+          const int ixc = ix0 * 3 + col;
+          const bool ok = row_ok && ixc >= 0 && ixc < p.W * 3;
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(s_patch + row * (PW * 3) + col);
+          const int nbytes = ok ? 4 : 0;                 // 0 -> the 4 bytes are zero-filled
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst),
+                       "l"(src + (ok ? ixc : 0)), "r"(nbytes)
+                       : "memory");
+        }
       }
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- conv: 5 pixels x 16 channels per thread ----

@@ -93,6 +93,7 @@ struct TcParams {
   int ct_h, ct_w, step_h, step_w, org_h, org_w;   // origin = tile*step - org
   // fused max-pool (0 = none, else window 2 or 3; stride 2): pooled tile pt_h x pt_w, pooled dims
   int pool, pt_h, pt_w, Hp, Wp;
+  int exp_mode;         // timing experiments only (SQDET_TC_EXP): 1 no fence, 2 no store, 4 no STS
   long long* dbg;       // optional per-CTA cycle counters (SQDET_TC_DEBUG=1), else null
   int y_cstride, relu;
   int lo_row_offset;    // rows between the hi and the lo copy of the packed weights
@@ -587,11 +588,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 float4 v;
                 v.x = fmaxf(o[0], lo_clip); v.y = fmaxf(o[1], lo_clip);
                 v.z = fmaxf(o[2], lo_clip); v.w = fmaxf(o[3], lo_clip);
-                *reinterpret_cast<float4*>(tile_w + lane * 128 + ((k ^ (lane & 7)) << 4)) = v;
+                if (!(p.exp_mode & 4))
+                  *reinterpret_cast<float4*>(tile_w + lane * 128 + ((k ^ (lane & 7)) << 4)) = v;
               }
-              fence_async_proxy();
+              if (!(p.exp_mode & 1)) fence_async_proxy();
               __syncwarp();
-              if (lane == 0)
+              if (lane == 0 && !(p.exp_mode & 2))
                 tma_store_4d(tile_w, &p.tmY, ck.y_coff + jg * 32, w0, h0 + 2 * q, img);
               ++n_store;
             }
@@ -1001,6 +1003,14 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     debug = d ? atoi(d) : 0;
   }
   TcParams prm = im->prm;
+  {
+    static int exp_mode = -1;
+    if (exp_mode < 0) {
+      const char* x = getenv("SQDET_TC_EXP");
+      exp_mode = x ? atoi(x) : 0;
+    }
+    prm.exp_mode = exp_mode;
+  }
   long long* dbg = nullptr;
   const int nb = (int)im->grid.x;
   if (debug) {
