@@ -76,6 +76,7 @@ struct TcChunk {
 struct TcParams {
   CUtensorMap tmA;
   CUtensorMap tmW;
+  CUtensorMap tmWs;     // weight slice map for cluster multicast: box {KC, 2N/cluster} rows
   CUtensorMap tmY;      // output tensor, box {32 ch, 16 w, 8 h, 1}, SWIZZLE_128B (TMA-store epilogue)
   const float* bias;    // may be null
   const float* scale;   // may be null (frozen BN)
@@ -93,6 +94,7 @@ struct TcParams {
   int ct_h, ct_w, step_h, step_w, org_h, org_w;   // origin = tile*step - org
   // fused max-pool (0 = none, else window 2 or 3; stride 2): pooled tile pt_h x pt_w, pooled dims
   int pool, pt_h, pt_w, Hp, Wp;
+  int cluster;          // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast across it
   int exp_mode;         // timing experiments only (SQDET_TC_EXP): 1 no fence, 2 no store, 4 no STS
   long long* dbg;       // optional per-CTA cycle counters (SQDET_TC_DEBUG=1), else null
   int y_cstride, relu;
@@ -187,6 +189,32 @@ __device__ __forceinline__ void pool_unit(const uint8_t* conv_base, uint8_t* poo
 }
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// 2-D TMA load multicast to every CTA of the cluster in `mask` (same smem offset and same
+// mbarrier offset in each destination CTA).
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                               int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -321,14 +349,22 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       (reinterpret_cast<uintptr_t>(s_par + 2 * 3 * MAX_N) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_items = p.ntiles * p.nchunks;
+  // Work decomposition: a cluster of C CTAs walks "super-items" = C consecutive tiles of one
+  // chunk in lockstep, so that every weight tile is fetched from L2 once per cluster and
+  // multicast into all C shared memories.  Tiles past the end are clamped (recomputed, not stored).
+  const int C = p.cluster;
+  const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
+  const int cid = (int)blockIdx.x / C, n_clusters = (int)gridDim.x / C;
+  const int spc = (p.ntiles + C - 1) / C;              // super-items per chunk
+  const int total_items = spc * p.nchunks;             // super-items
+  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
   const int G = p.seg_stages;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&split[s], 128);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], (uint32_t)C);     // one tcgen05.commit arrival from every CTA
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
@@ -339,6 +375,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();           // peers' barriers exist before anyone multicasts
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -355,9 +392,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       uint32_t st_ph = 0;
       long long w_empty = 0;
       const long long t_begin = clock64();
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const TcChunk ck = p.chunk[item / p.ntiles];
-        int tile = item % p.ntiles;
+      for (int item = cid; item < total_items; item += n_clusters) {
+        const TcChunk ck = p.chunk[item / spc];
+        int tile = (item % spc) * C + (int)crank;
+        if (tile >= p.ntiles) tile = p.ntiles - 1;
         const int tw = tile % p.tiles_w;
         tile /= p.tiles_w;
         const int h0 = (tile % p.tiles_h) * p.step_h - p.org_h, w0 = tw * p.step_w - p.org_w;
@@ -375,8 +413,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           const int dy = tap / ck.ksize, dx = tap - dy * ck.ksize;
           tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
           const int row = ck.w_row_base + i * p.N;
-          tma_load_2d(st + A_BYTES, &p.tmW, &full[s], 0, row);
-          tma_load_2d(st + A_BYTES + B_BYTES, &p.tmW, &full[s], 0, row + p.lo_row_offset);
+          if (C == 1) {
+            tma_load_2d(st + A_BYTES, &p.tmW, &full[s], 0, row);
+            tma_load_2d(st + A_BYTES + B_BYTES, &p.tmW, &full[s], 0, row + p.lo_row_offset);
+          } else {
+            // this CTA fetches slice `crank` of the stacked [hi (N rows); lo (N rows)] tile and
+            // multicasts it to the whole cluster
+            const int srows = 2 * p.N / C;
+            const int r0 = (int)crank * srows;
+            const int which = r0 / p.N, rr = r0 - which * p.N;
+            tma_load_2d_mc(st + A_BYTES + which * B_BYTES + rr * KC * 4, &p.tmWs, &full[s], 0,
+                           row + rr + which * p.lo_row_offset, cmask);
+          }
         }
       }
       if (p.dbg) {
@@ -399,8 +447,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       int it = 0, g = 0, st_i = 0;
       uint32_t st_ph = 0;
       long long w_split = 0, w_tempty = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const TcChunk ck = p.chunk[item / p.ntiles];
+      for (int item = cid; item < total_items; item += n_clusters) {
+        const TcChunk ck = p.chunk[item / spc];
         const int iters = ck.ksize * ck.ksize * p.kch;
         for (int i0 = 0; i0 < iters; i0 += G, ++g) {
           const int buf = g & 1;
@@ -430,7 +478,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 umma_tf32_ts(d_tmem, a_hi + 8 * j, dbl, idesc, 1u);
                 umma_tf32_ts(d_tmem, a_hi + 8 * j, dbh, idesc, 1u);
               }
-              umma_commit(&empty[s]);    // frees the smem stage once these MMAs have read it
+              if (C == 1) umma_commit(&empty[s]);   // frees the smem stage once the MMAs read it
+              else umma_commit_mc(&empty[s], cmask);   // ... in every CTA of the cluster
             }
             __syncwarp();
           }
@@ -451,8 +500,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     int it = 0, st_i = 0;
     uint32_t st_ph = 0;
     long long w_full = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const TcChunk ck = p.chunk[item / p.ntiles];
+    for (int item = cid; item < total_items; item += n_clusters) {
+      const TcChunk ck = p.chunk[item / spc];
       const int iters = ck.ksize * ck.ksize * p.kch;
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = st_i;
@@ -498,9 +547,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     int g = 0;
     long long w_tfull = 0, c_epi = 0, c_stw = 0, c_pool = 0, c_par = 0;
     int n_item = 0, n_store = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const TcChunk ck = p.chunk[item / p.ntiles];
-      int tile = item % p.ntiles;
+    for (int item = cid; item < total_items; item += n_clusters) {
+      const TcChunk ck = p.chunk[item / spc];
+      int tile = (item % spc) * C + (int)crank;
+      const bool tile_valid = tile < p.ntiles;
+      if (!tile_valid) tile = p.ntiles - 1;
       const int tw = tile % p.tiles_w;
       tile /= p.tiles_w;
       const int th_i = tile % p.tiles_h;
@@ -593,7 +644,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               }
               if (!(p.exp_mode & 1)) fence_async_proxy();
               __syncwarp();
-              if (lane == 0 && !(p.exp_mode & 2))
+              if (lane == 0 && tile_valid && !(p.exp_mode & 2))
                 tma_store_4d(tile_w, &p.tmY, ck.y_coff + jg * 32, w0, h0 + 2 * q, img);
               ++n_store;
             }
@@ -651,13 +702,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           if (p.dbg) c_pool += clock64() - tp0;
           fence_async_proxy();
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (issuer) {
+          if (issuer && tile_valid) {
             for (int jg = 0; jg * 32 < ck.ch_count; ++jg)
               tma_store_4d(pool_base + jg * 4096, &p.tmY, ck.y_coff + jg * 32, tw * 8,
                            th_i * p.pt_h, img);
           }
         }
-      } else if (pix_ok) {
+      } else if (pix_ok && tile_valid) {
         float* yrow =
             p.y + (((size_t)img * p.Ho + oh) * p.Wo + ow) * (size_t)p.y_cstride + ck.y_coff;
         // 256-bit stores: each thread writes whole 32-byte sectors of its pixel's channel run.
@@ -712,6 +763,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();           // no CTA leaves while peers may still multicast to it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -913,9 +965,20 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long items = (long long)P.ntiles * P.nchunks;
-    const long long slots = (long long)sms * ctas;
-    im->grid = dim3((unsigned)(items < slots ? items : slots));
+    // Cluster size for the weight multicast: 2 packs all 148 SMs (74 TPC pairs); 4 quarters the
+    // L2->SM weight traffic but strands SMs of GPCs whose SM count is not a multiple of 4.
+    static int env_cluster = -1;
+    if (env_cluster < 0) {
+      const char* a = getenv("SQDET_TC_CLUSTER");
+      env_cluster = a ? atoi(a) : 2;
+    }
+    int cluster = (env_cluster == 4 || env_cluster == 2) ? env_cluster : 1;
+    if (P.ntiles < cluster) cluster = 1;
+    P.cluster = cluster;
+    const long long supers = (long long)((P.ntiles + cluster - 1) / cluster) * P.nchunks;
+    long long nclusters = (long long)(sms * ctas) / cluster;
+    if (supers < nclusters) nclusters = supers;
+    im->grid = dim3((unsigned)(nclusters * cluster));
   }
   P.y = y_dev;
   SQ_CUDA(cudaMalloc(&im->d_w, sizeof(float) * (size_t)row * 2 * KC));
@@ -956,6 +1019,10 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   }
   rc = encode_w_map(&P.tmW, im->d_w, row * 2, KC, N);
   if (rc) return rc;
+  if (P.cluster > 1) {
+    rc = encode_w_map(&P.tmWs, im->d_w, row * 2, KC, 2 * N / P.cluster);
+    if (rc) return rc;
+  }
   // opt in to the full 227 KB once for both instantiations (the attribute is per function,
   // not per launch, so it must cover the largest plan)
   static bool attr_set = false;
@@ -1018,10 +1085,23 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     SQ_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 12 * nb, stream));
     prm.dbg = dbg;
   }
-  if (im->KC == 32)
-    conv_tc_kernel<32><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
-  else
-    conv_tc_kernel<16><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = im->grid;
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = im->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)prm.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = (im->KC == 32) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<32>, prm)
+                                    : cudaLaunchKernelEx(&cfg, conv_tc_kernel<16>, prm);
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(conv_tc_kernel)");
+  }
   SQ_CHECK_LAUNCH("conv_tc_kernel");
   if (debug) {
     std::vector<long long> h((size_t)12 * nb);
@@ -1032,10 +1112,10 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     for (int b = 0; b < nb; ++b)
       for (int k = 0; k < 12; ++k) a[k] += (double)h[(size_t)b * 12 + k] / nb;
     fprintf(stderr,
-            "[tc] grid %d smem %zu KC %d N %d kch %d chunks %d stages %d seg %d | per-CTA avg cycles: "
+            "[tc] grid %d cluster %d smem %zu KC %d N %d kch %d chunks %d stages %d seg %d | per-CTA avg cycles: "
             "total %.0f stages %.0f | waits: producer(empty) %.0f mma(split) %.0f mma(tempty) %.0f "
             "splitter(full) %.0f drain(tfull) %.0f | epilogue %.0f (store-wait %.0f, pool %.0f, params %.0f)\n",
-            nb, im->smem_bytes, im->KC, prm.N, prm.kch, prm.nchunks, prm.stages, prm.seg_stages,
+            nb, prm.cluster, im->smem_bytes, im->KC, prm.N, prm.kch, prm.nchunks, prm.stages, prm.seg_stages,
             a[5], a[6], a[0], a[1], a[2], a[3], a[4], a[7], a[8], a[9], a[10]);
   }
   return SQDET_OK;
