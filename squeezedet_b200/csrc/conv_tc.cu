@@ -970,7 +970,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     static int env_cluster = -1;
     if (env_cluster < 0) {
       const char* a = getenv("SQDET_TC_CLUSTER");
-      env_cluster = a ? atoi(a) : 2;
+      env_cluster = a ? atoi(a) : 1;   // measured: multicast (2, 4) is slower, see DESIGN.md
     }
     int cluster = (env_cluster == 4 || env_cluster == 2) ? env_cluster : 1;
     if (P.ntiles < cluster) cluster = 1;
