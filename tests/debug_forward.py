@@ -10,7 +10,9 @@ from squeezedet_b200.utils import synth
 net = sys.argv[1] if len(sys.argv) > 1 else 'squeezeDet'
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 cls, cf = {'squeezeDet': ('SqueezeDet', 'kitti_squeezeDet_config'),
-           'squeezeDet+': ('SqueezeDetPlus', 'kitti_squeezeDetPlus_config')}[net]
+           'squeezeDet+': ('SqueezeDetPlus', 'kitti_squeezeDetPlus_config'),
+           'vgg16': ('VGG16ConvDet', 'kitti_vgg16_config'),
+           'resnet50': ('ResNet50ConvDet', 'kitti_res50_config')}[net]
 mc = getattr(cfg, cf)()
 mc.IMAGE_WIDTH, mc.IMAGE_HEIGHT, mc.BATCH_SIZE = 1242, 375, batch
 mc.ANCHOR_BOX = cfg.set_anchors(mc)
