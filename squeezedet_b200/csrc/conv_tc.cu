@@ -33,9 +33,11 @@
 // Persistent CTAs (one per SM, 384 threads = 3 warpgroups), static round-robin over
 //   (chunk, tile) items:  warpgroup 0: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
 //   (one elected lane), warps 2-3 idle;  warpgroup 1 = operand splitter;  warpgroup 2 =
-//   segment drain + epilogue (tcgen05.ld -> fp32 add -> +bias [*scale+shift] -> relu ->
-//   256-bit global stores).  setmaxnreg moves registers from warpgroups 0/1 to the drain
-//   warpgroup, whose 128 running sums per thread must stay out of local memory.
+//   segment drain + epilogue (tcgen05.ld -> fp32 add -> +bias [*scale+shift] -> relu -> TMA
+//   store); TWO drain warpgroups alternate items (measured: one drain group was the bottleneck
+//   of the small-K layers - the MMA warp spent 30-45 % of its time waiting for TMEM buffers).
+//   setmaxnreg moves registers from warpgroups 0/1 to the drain warpgroups, whose running sums
+//   (up to 128 per thread) must stay out of local memory.
 // Pipelines: full[s] (TMA -> splitter), split[s] (splitter -> MMA), empty[s]
 //   (tcgen05.commit -> TMA), tfull[b] (tcgen05.commit -> drain), tempty[b] (drain -> MMA).
 // Roofline: SqueezeDet fire2-9 are HBM-bound even fused (AI 24-95 FLOP/B fp32 I/O),
@@ -58,7 +60,7 @@ namespace sqdet {
 namespace {
 
 constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;   // 128 pixels
-constexpr int NUM_THREADS = 384;       // 3 warpgroups: {TMA, MMA, 2 spare} | splitter | drain
+constexpr int NUM_THREADS = 512;       // 4 warpgroups: {TMA, MMA, 2 spare} | splitter | drain A | drain B
 constexpr int MAX_CHUNKS = 16;
 constexpr int MAX_N = 128;          // output channels per item (register-resident running sums)
 constexpr int MAX_STAGES = 8;
@@ -343,10 +345,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   uint64_t* tempty = tfull + 2;             // [2]  drain -> MMA (buffer read out)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   // per-item epilogue parameters (bias, scale, shift), double-buffered by item parity
-  float* s_par = reinterpret_cast<float*>(tempty + 4);   // [2][3][MAX_N]
+  float* s_par = reinterpret_cast<float*>(tempty + 4);   // [2 groups][2][3][MAX_N]
   // two 16 KB output staging tiles (128 pixels x 32 channels, 128B-swizzled) for TMA stores
   uint8_t* s_out = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(s_par + 2 * 3 * MAX_N) + 1023) & ~uintptr_t(1023));
+      (reinterpret_cast<uintptr_t>(s_par + 4 * 3 * MAX_N) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work decomposition: a cluster of C CTAs walks "super-items" = C consecutive tiles of one
@@ -384,7 +386,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   // Items are ordered chunk-major (all tiles of chunk 0, then chunk 1, ...) so that the static
   // round-robin gives every CTA the same mix of cheap (1x1) and expensive (3x3) items.
   if (warp < 4) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // one instruction for the whole warpgroup
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");   // one instruction for the whole warpgroup
    if (warp == 0) {
     // ================================ TMA producer =====================================
     if (lane == 0) {
@@ -495,7 +497,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
    }   // warps 2-3 of warpgroup 0 are spare: straight to the teardown barrier
   } else if (warp < 8) {
     // ================================ operand splitter ====================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     const int t = threadIdx.x - 128;   // 0..127
     int it = 0, st_i = 0;
     uint32_t st_ph = 0;
@@ -540,15 +542,25 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     if (p.dbg && t == 0) p.dbg[blockIdx.x * 12 + 3] = w_full;
   } else {
     // ============================ segment drain + epilogue ================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    // two drain groups (warps 8-11 and 12-15) take alternate items; the fused-pool epilogue
+    // needs a CTA-sized staging area, so there group 0 takes every item
+    const int dgroup = (warp >= 12) ? 1 : 0;
+    const int ngroups = p.pool ? 1 : 2;
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                 // accumulator row = pixel within the tile
+    const int tt = threadIdx.x - 256 - 128 * dgroup;   // 0..127 within the drain group
     float acc[MAX_N];
     int g = 0;
     long long w_tfull = 0, c_epi = 0, c_stw = 0, c_pool = 0, c_par = 0;
-    int n_item = 0, n_store = 0;
-    for (int item = cid; item < total_items; item += n_clusters) {
+    int n_item = 0, n_own = 0, n_store = 0;
+    for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
       const TcChunk ck = p.chunk[item / spc];
+      const int iters = ck.ksize * ck.ksize * p.kch;
+      if ((n_item % ngroups) != dgroup || (p.pool && dgroup == 1)) {
+        g += (iters + G - 1) / G;                // segments of an item the other group drains
+        continue;
+      }
       int tile = (item % spc) * C + (int)crank;
       const bool tile_valid = tile < p.ntiles;
       if (!tile_valid) tile = p.ntiles - 1;
@@ -557,43 +569,34 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const int th_i = tile % p.tiles_h;
       const int h0 = th_i * p.step_h - p.org_h, w0 = tw * p.step_w - p.org_w;
       const int img = tile / p.tiles_h;
-      const int iters = ck.ksize * ck.ksize * p.kch;
       const int ncols = (ck.ch_count + 15) & ~15;
       // stage this item's bias / scale / shift in smem (one element per drain thread); the
       // named barrier also orders it against the previous item's epilogue reads.
-      float* par = s_par + (n_item & 1) * 3 * MAX_N;
+      float* par = s_par + (dgroup * 2 + (n_own & 1)) * 3 * MAX_N;
       const long long tpar0 = p.dbg ? clock64() : 0;
       {
-        const int tt = threadIdx.x - 256;
         const bool in = tt < ck.ch_count;
         par[tt] = (in && p.bias) ? __ldg(p.bias + ck.bias_base + tt) : 0.f;
         par[MAX_N + tt] = (in && p.scale) ? __ldg(p.scale + ck.bias_base + tt) : 1.f;
         par[2 * MAX_N + tt] = (in && p.scale) ? __ldg(p.shift + ck.bias_base + tt) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + dgroup) : "memory");
       }
       if (p.dbg) c_par += clock64() - tpar0;
-      ++n_item;
+      ++n_own;
       for (int i0 = 0; i0 < iters; i0 += G, ++g) {
         const int buf = g & 1;
         SQ_TIMED_WAIT(w_tfull, &tfull[buf], ((uint32_t)g >> 1) & 1u);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.N);
 #pragma unroll
-        for (int c0 = 0; c0 < MAX_N; c0 += 32) {
+        for (int c0 = 0; c0 < MAX_N; c0 += 16) {
           if (c0 < ncols) {                      // warp-uniform
-            uint32_t v0[16], v1[16];
+            uint32_t v0[16];
             tmem_ld16_nowait(trow + (uint32_t)c0, v0);
-            const bool second = (c0 + 16 < ncols);
-            if (second) tmem_ld16_nowait(trow + (uint32_t)(c0 + 16), v1);
             tmem_wait_ld();
 #pragma unroll
             for (int e = 0; e < 16; ++e)
               acc[c0 + e] = (i0 == 0 ? 0.f : acc[c0 + e]) + __uint_as_float(v0[e]);
-            if (second) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e)
-                acc[c0 + 16 + e] = (i0 == 0 ? 0.f : acc[c0 + 16 + e]) + __uint_as_float(v1[e]);
-            }
           }
         }
         tc_fence_before();
@@ -610,7 +613,6 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         // tiles / the channel tail; the drain warps never wait on global memory.
         const bool affine = p.scale != nullptr;
         const float lo_clip = p.relu ? 0.f : -CUDART_INF_F;
-        const int tt = threadIdx.x - 256;
         if (!p.pool) {
           // ---- plain: each warp owns tile rows 2q, 2q+1 (its 32 TMEM lanes) and stores them
           // itself: no CTA-level barrier, only __syncwarp.  Ring of two 4 KB tiles per warp.
@@ -623,7 +625,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 if (p.dbg) c_stw += clock64() - t0;
               }
               __syncwarp();
-              uint8_t* tile_w = s_out + q * 8192 + (n_store & 1) * 4096;
+              uint8_t* tile_w = s_out + (dgroup * 4 + q) * 8192 + (n_store & 1) * 4096;
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int c = jg * 32 + k * 4;
@@ -639,12 +641,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 float4 v;
                 v.x = fmaxf(o[0], lo_clip); v.y = fmaxf(o[1], lo_clip);
                 v.z = fmaxf(o[2], lo_clip); v.w = fmaxf(o[3], lo_clip);
-                if (!(p.exp_mode & 4))
-                  *reinterpret_cast<float4*>(tile_w + lane * 128 + ((k ^ (lane & 7)) << 4)) = v;
+                *reinterpret_cast<float4*>(tile_w + lane * 128 + ((k ^ (lane & 7)) << 4)) = v;
               }
-              if (!(p.exp_mode & 1)) fence_async_proxy();
+              fence_async_proxy();
               __syncwarp();
-              if (lane == 0 && tile_valid && !(p.exp_mode & 2))
+              if (lane == 0 && tile_valid)
                 tma_store_4d(tile_w, &p.tmY, ck.y_coff + jg * 32, w0, h0 + 2 * q, img);
               ++n_store;
             }
@@ -658,7 +659,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             tma_store_wait_read_all();                    // previous item's pooled tiles are free
             if (p.dbg) c_stw += clock64() - t0;
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + dgroup) : "memory");
           const float ninf = -CUDART_INF_F;
 #pragma unroll
           for (int jg = 0; jg < MAX_N / 32; ++jg) {
@@ -686,7 +687,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               }
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + dgroup) : "memory");
           const long long tp0 = p.dbg ? clock64() : 0;
           // unit = (channel group jg, pooled pixel pp, 16-byte chunk k2); pt_w == 8
           const int n_pp = p.pt_h * 8;
@@ -701,7 +702,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           }
           if (p.dbg) c_pool += clock64() - tp0;
           fence_async_proxy();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + dgroup) : "memory");
           if (issuer && tile_valid) {
             for (int jg = 0; jg * 32 < ck.ch_count; ++jg)
               tma_store_4d(pool_base + jg * 4096, &p.tmY, ck.y_coff + jg * 32, tw * 8,
@@ -753,7 +754,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       if (p.dbg) c_epi += clock64() - t_epi;
     }
     if (p.tma_store && lane == 0) tma_store_wait_all();
-    if (p.dbg && threadIdx.x == 256) {
+    if (p.dbg && threadIdx.x == 256) {   // group 0 only
       p.dbg[blockIdx.x * 12 + 4] = w_tfull;
       p.dbg[blockIdx.x * 12 + 7] = c_epi;
       p.dbg[blockIdx.x * 12 + 8] = c_stw;
@@ -938,8 +939,8 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     const char* c = getenv("SQDET_TC_SEG");    env_seg = c ? atoi(c) : 0;
   }
   int ctas = env_ctas > 0 ? env_ctas : 1;   // 384 threads x 168 regs: one CTA per SM
-  const size_t overhead = 1024 /*alignment*/ + 512 /*barriers*/ + 2 * 3 * MAX_N * 4 /*epilogue params*/ +
-                          1024 + (pooled ? (MAX_N / 32) * (16384 + 4096) : 4 * 8192) /*store staging*/;
+  const size_t overhead = 1024 /*alignment*/ + 512 /*barriers*/ + 4 * 3 * MAX_N * 4 /*epilogue params*/ +
+                          1024 + (pooled ? (MAX_N / 32) * (16384 + 4096) : 8 * 8192) /*store staging*/;
   int stages = 0;
   for (; ctas >= 1; --ctas) {
     const size_t budget = (ctas == 1 ? 227 * 1024 : (227 * 1024) / ctas - 1024) - overhead;
@@ -1085,7 +1086,13 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     SQ_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 12 * nb, stream));
     prm.dbg = dbg;
   }
-  {
+  if (prm.cluster <= 1) {
+    // classic launch (no cluster attribute: keeps the non-cluster CTA->SM placement path)
+    if (im->KC == 32)
+      conv_tc_kernel<32><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+    else
+      conv_tc_kernel<16><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+  } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = im->grid;
     cfg.blockDim = dim3(NUM_THREADS);
