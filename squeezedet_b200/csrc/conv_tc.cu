@@ -341,8 +341,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   uint64_t* full = bars;                    // [S]  TMA -> splitter
   uint64_t* split = bars + MAX_STAGES;      // [S]  splitter -> MMA
   uint64_t* empty = bars + 2 * MAX_STAGES;  // [S]  MMA -> TMA
-  uint64_t* tfull = bars + 3 * MAX_STAGES;  // [2]  MMA -> drain (segment accumulated)
-  uint64_t* tempty = tfull + 2;             // [2]  drain -> MMA (buffer read out)
+  // tfull is per (drain group, TMEM buffer): an mbarrier waiter must observe every phase in
+  // order, so each group gets barriers only it waits on; tempty's only waiter is the MMA warp.
+  uint64_t* tfull = bars + 3 * MAX_STAGES;  // [2 groups][2]  MMA -> drain (segment accumulated)
+  uint64_t* tempty = tfull + 4;             // [2]  drain -> MMA (buffer read out)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   // per-item epilogue parameters (bias, scale, shift), double-buffered by item parity
   float* s_par = reinterpret_cast<float*>(tempty + 4);   // [2 groups][2][3][MAX_N]
@@ -368,8 +370,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       mbar_init(&split[s], 128);
       mbar_init(&empty[s], (uint32_t)C);     // one tcgen05.commit arrival from every CTA
     }
+    for (int b = 0; b < 4; ++b) mbar_init(&tfull[b], 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -446,12 +448,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
       const uint64_t desc_hi = make_desc<KC>(0) & 0xFFFFFFFF00000000ull;   // layout/SBO/version
       const uint32_t desc_lo0 = (uint32_t)(make_desc<KC>(0) & 0xFFFFFFFFull);  // LBO field
-      int it = 0, g = 0, st_i = 0;
+      int it = 0, g = 0, st_i = 0, n_item = 0;
       uint32_t st_ph = 0;
       long long w_split = 0, w_tempty = 0;
-      for (int item = cid; item < total_items; item += n_clusters) {
+      for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
         const TcChunk ck = p.chunk[item / spc];
         const int iters = ck.ksize * ck.ksize * p.kch;
+        const int owner = p.pool ? 0 : (n_item & 1);      // drain group of this item
         for (int i0 = 0; i0 < iters; i0 += G, ++g) {
           const int buf = g & 1;
           SQ_TIMED_WAIT(w_tempty, &tempty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);   // buffer drained
@@ -485,7 +488,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             }
             __syncwarp();
           }
-          if (elect_one()) umma_commit(&tfull[buf]);    // segment complete -> drain warps
+          if (elect_one()) umma_commit(&tfull[owner * 2 + buf]);   // segment complete -> its drain group
           __syncwarp();
         }
       }
@@ -554,6 +557,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     int g = 0;
     long long w_tfull = 0, c_epi = 0, c_stw = 0, c_pool = 0, c_par = 0;
     int n_item = 0, n_own = 0, n_store = 0;
+    uint32_t use[2] = {0u, 0u};                  // own segments seen per TMEM buffer
     for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
       const TcChunk ck = p.chunk[item / spc];
       const int iters = ck.ksize * ck.ksize * p.kch;
@@ -585,7 +589,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       ++n_own;
       for (int i0 = 0; i0 < iters; i0 += G, ++g) {
         const int buf = g & 1;
-        SQ_TIMED_WAIT(w_tfull, &tfull[buf], ((uint32_t)g >> 1) & 1u);
+        SQ_TIMED_WAIT(w_tfull, &tfull[dgroup * 2 + buf], use[buf] & 1u);
+        ++use[buf];
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.N);
 #pragma unroll
