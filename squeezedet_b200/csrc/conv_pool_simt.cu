@@ -29,6 +29,14 @@ constexpr int CT_H = 2 * PT_H + 1, CT_W = 2 * PT_W + 1;   // 9 x 33 conv pixels 
 constexpr int CT_PIX = CT_H * CT_W;               // 297
 constexpr int PIX_PER_THREAD = (CT_PIX + 63) / 64;  // 5
 
+// Two IEEE fp32 FMAs per instruction (Blackwell FFMA2): identical results to two fmaf().
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b,
+                                                    unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 struct ConvPoolParams {
   const float* x;       // [B,H,W,3]
   const float* w;       // [k,k,3,Cout]
@@ -102,11 +110,11 @@ conv_pool_simt_kernel(const ConvPoolParams p) {
   // ---- conv: 5 pixels x 16 channels per thread ----
   const int cg = tid >> 6;                 // channel group (warp-uniform)
   const int l64 = tid & 63;
-  float acc[PIX_PER_THREAD][16];
+  unsigned long long acc2[PIX_PER_THREAD][8];      // 16 channels as 8 packed fp32 pairs
 #pragma unroll
   for (int i = 0; i < PIX_PER_THREAD; ++i)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[i][c] = 0.f;
+    for (int c = 0; c < 8; ++c) acc2[i][c] = 0ull;
   int pbase[PIX_PER_THREAD];
 #pragma unroll
   for (int i = 0; i < PIX_PER_THREAD; ++i) {
@@ -120,20 +128,28 @@ conv_pool_simt_kernel(const ConvPoolParams p) {
 #pragma unroll
     for (int bc = 0; bc < KS * 3; ++bc) {          // (b, c) flattened: contiguous in the patch
       const int k = a * KS * 3 + bc;
-      const float4 w0 = *reinterpret_cast<const float4*>(wg + k * p.Cout);
-      const float4 w1 = *reinterpret_cast<const float4*>(wg + k * p.Cout + 4);
-      const float4 w2 = *reinterpret_cast<const float4*>(wg + k * p.Cout + 8);
-      const float4 w3 = *reinterpret_cast<const float4*>(wg + k * p.Cout + 12);
-      const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
-                            w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+      const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout);
+      const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout + 4);
+      const ulonglong2 wc = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout + 8);
+      const ulonglong2 wd = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout + 12);
+      const unsigned long long wv[8] = {wa.x, wa.y, wb.x, wb.y, wc.x, wc.y, wd.x, wd.y};
 #pragma unroll
       for (int i = 0; i < PIX_PER_THREAD; ++i) {
-        const float xv = s_patch[pbase[i] + a * PW * 3 + bc];
+        const unsigned xb = __float_as_uint(s_patch[pbase[i] + a * PW * 3 + bc]);
+        const unsigned long long xx = ((unsigned long long)xb << 32) | xb;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[i][c] = fmaf(xv, wv[c], acc[i][c]);
+        for (int c = 0; c < 8; ++c) acc2[i][c] = ffma2(xx, wv[c], acc2[i][c]);
       }
     }
   }
+  float acc[PIX_PER_THREAD][16];
+#pragma unroll
+  for (int i = 0; i < PIX_PER_THREAD; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      acc[i][2 * c] = __uint_as_float((unsigned)(acc2[i][c] & 0xffffffffull));
+      acc[i][2 * c + 1] = __uint_as_float((unsigned)(acc2[i][c] >> 32));
+    }
 
   // ---- epilogue 1: bias [, affine], relu, mask, conv tile -> smem ----
   {
