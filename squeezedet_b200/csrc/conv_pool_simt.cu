@@ -128,17 +128,22 @@ conv_pool_simt_kernel(const ConvPoolParams p) {
 #pragma unroll
     for (int bc = 0; bc < KS * 3; ++bc) {          // (b, c) flattened: contiguous in the patch
       const int k = a * KS * 3 + bc;
-      const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout);
-      const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout + 4);
-      const ulonglong2 wc = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout + 8);
-      const ulonglong2 wd = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout + 12);
-      const unsigned long long wv[8] = {wa.x, wa.y, wb.x, wb.y, wc.x, wc.y, wd.x, wd.y};
+      unsigned long long xx[PIX_PER_THREAD];
 #pragma unroll
       for (int i = 0; i < PIX_PER_THREAD; ++i) {
         const unsigned xb = __float_as_uint(s_patch[pbase[i] + a * PW * 3 + bc]);
-        const unsigned long long xx = ((unsigned long long)xb << 32) | xb;
+        xx[i] = ((unsigned long long)xb << 32) | xb;
+      }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc2[i][c] = ffma2(xx, wv[c], acc2[i][c]);
+      for (int half = 0; half < 2; ++half) {       // 8 channels at a time: fewer live weights
+        const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout + half * 8);
+        const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(wg + k * p.Cout + half * 8 + 4);
+        const unsigned long long wv[4] = {wa.x, wa.y, wb.x, wb.y};
+#pragma unroll
+        for (int i = 0; i < PIX_PER_THREAD; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            acc2[i][half * 4 + c] = ffma2(xx[i], wv[c], acc2[i][half * 4 + c]);
       }
     }
   }

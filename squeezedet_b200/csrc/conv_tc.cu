@@ -73,6 +73,8 @@ struct TcChunk {
   int ch_count;     // valid output channels in this chunk
   int y_coff;       // channel offset of ch_base..ch_base+ch_count in the output tensor
   int bias_base;    // index of ch_base in the bias/scale/shift arrays
+  int tap_begin;    // first filter tap of this chunk (split-K partials cover tap sub-ranges)
+  int tap_count;    // number of taps (ksize*ksize unless split)
 };
 
 struct TcParams {
@@ -404,7 +406,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         tile /= p.tiles_w;
         const int h0 = (tile % p.tiles_h) * p.step_h - p.org_h, w0 = tw * p.step_w - p.org_w;
         const int img = tile / p.tiles_h;
-        const int iters = ck.ksize * ck.ksize * p.kch;
+        const int iters = ck.tap_count * p.kch;
         const uint32_t a_bytes = (uint32_t)(p.ct_h * p.ct_w * KC * 4);   // the TMA box
         for (int i = 0; i < iters; ++i, ++it) {
           const int s = st_i;
@@ -413,7 +415,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           SQ_TIMED_WAIT(w_empty, &empty[s], ph ^ 1u);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
           mbar_expect_tx(&full[s], a_bytes + (uint32_t)(2 * B_BYTES));
-          const int tap = i / p.kch, kc = i - tap * p.kch;
+          const int tl = i / p.kch, kc = i - tl * p.kch;
+          const int tap = ck.tap_begin + tl;
           const int dy = tap / ck.ksize, dx = tap - dy * ck.ksize;
           tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
           const int row = ck.w_row_base + i * p.N;
@@ -453,7 +456,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       long long w_split = 0, w_tempty = 0;
       for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
         const TcChunk ck = p.chunk[item / spc];
-        const int iters = ck.ksize * ck.ksize * p.kch;
+        const int iters = ck.tap_count * p.kch;
         const int owner = p.pool ? 0 : (n_item & 1);      // drain group of this item
         for (int i0 = 0; i0 < iters; i0 += G, ++g) {
           const int buf = g & 1;
@@ -507,7 +510,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     long long w_full = 0;
     for (int item = cid; item < total_items; item += n_clusters) {
       const TcChunk ck = p.chunk[item / spc];
-      const int iters = ck.ksize * ck.ksize * p.kch;
+      const int iters = ck.tap_count * p.kch;
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = st_i;
         const uint32_t ph = st_ph;
@@ -560,7 +563,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     uint32_t use[2] = {0u, 0u};                  // own segments seen per TMEM buffer
     for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
       const TcChunk ck = p.chunk[item / spc];
-      const int iters = ck.ksize * ck.ksize * p.kch;
+      const int iters = ck.tap_count * p.kch;
       if ((n_item % ngroups) != dgroup || (p.pool && dgroup == 1)) {
         g += (iters + G - 1) / G;                // segments of an item the other group drains
         continue;
@@ -776,6 +779,38 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
+// Split-K reduction: y[p][c] = act( (bias[c] + sum_s part[p][s*pitch + c]) [*scale + shift] ).
+// Deterministic (fixed summation order), 128-bit loads/stores; the partials are L2-resident.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ y,
+                     const float* __restrict__ bias, const float* __restrict__ scale,
+                     const float* __restrict__ shift, long long npix, int cout, int pitch,
+                     int ksplit, int y_cstride, int y_coff, int relu) {
+  const int c4n = cout / 4;
+  const long long total = npix * c4n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    const long long px = idx / c4n;
+    float4 a = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = part + px * (long long)(ksplit * pitch) + c;
+    for (int s2 = 0; s2 < ksplit; ++s2) {
+      const float4 v = *reinterpret_cast<const float4*>(src + s2 * pitch);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (scale) {
+      const float4 sc = *reinterpret_cast<const float4*>(scale + c);
+      const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+      a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y;
+      a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
+    }
+    if (relu) {
+      a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(y + px * y_cstride + y_coff + c) = a;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -798,6 +833,7 @@ static EncodeTiledFn get_encode() {
 
 struct ConvGroup {        // one conv reading the shared input; >= 1 chunks
   int ksize, Cout, y_coff, bias_base;
+  int tap_begin = 0, tap_count = -1;   // tap sub-range (split-K); -1 = all ksize*ksize taps
 };
 
 struct TcImpl {
@@ -814,6 +850,12 @@ struct TcImpl {
   int bias_total = 0;
   std::vector<ConvGroup> groups;
   std::vector<TcChunk> chunks;
+  // split-K: the kernel writes `ksplit` partial sums into d_scratch [pixels][ksplit*pitch];
+  // splitk_reduce_kernel adds them (+bias [,affine], relu) into the real output
+  int ksplit = 1, pitch = 0, relu_final = 0, cout = 0, y_cstride_final = 0, y_coff_final = 0;
+  long long npix = 0;
+  float* d_scratch = nullptr;
+  float* y_final = nullptr;
 };
 
 static inline float host_rn_tf32(float x) {
@@ -895,7 +937,9 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
       c.ch_count = (g.Cout - cb) < N ? (g.Cout - cb) : N;
       c.y_coff = g.y_coff + cb;
       c.bias_base = g.bias_base + cb;
-      row += g.ksize * g.ksize * kch * N;
+      c.tap_begin = g.tap_begin;
+      c.tap_count = g.tap_count < 0 ? g.ksize * g.ksize : g.tap_count;
+      row += c.tap_count * kch * N;
       im->chunks.push_back(c);
     }
   }
@@ -1052,10 +1096,11 @@ static void pack_group(const TcImpl* im, int gi, const float* w_hwio, std::vecto
   for (int i = 0; i < gi; ++i) ci += (im->groups[i].Cout + N - 1) / N;
   for (int cb = 0; cb < g.Cout; cb += N, ++ci) {
     const TcChunk& c = im->chunks[ci];
-    for (int tap = 0; tap < g.ksize * g.ksize; ++tap)
+    for (int tl = 0; tl < c.tap_count; ++tl)
       for (int kc = 0; kc < kch; ++kc)
         for (int n = 0; n < c.ch_count; ++n) {
-          const size_t rowi = (size_t)c.w_row_base + ((size_t)tap * kch + kc) * N + n;
+          const int tap = c.tap_begin + tl;
+          const size_t rowi = (size_t)c.w_row_base + ((size_t)tl * kch + kc) * N + n;
           for (int k = 0; k < KC; ++k) {
             const float v = w_hwio[((size_t)tap * Cin + (size_t)kc * KC + k) * g.Cout + cb + n];
             const float hi = host_rn_tf32(v);
@@ -1115,6 +1160,15 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(conv_tc_kernel)");
   }
   SQ_CHECK_LAUNCH("conv_tc_kernel");
+  if (im->ksplit > 1) {
+    const long long total = im->npix * (im->cout / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+        im->d_scratch, im->y_final, im->d_bias, im->d_scale, im->d_shift, im->npix, im->cout,
+        im->pitch, im->ksplit, im->y_cstride_final, im->y_coff_final, im->relu_final);
+    SQ_CHECK_LAUNCH("splitk_reduce_kernel");
+  }
   if (debug) {
     std::vector<long long> h((size_t)12 * nb);
     SQ_CUDA(cudaStreamSynchronize(stream));
@@ -1140,6 +1194,7 @@ static void release_impl(void** impl) {
   cudaFree(im->d_bias);
   cudaFree(im->d_scale);
   cudaFree(im->d_shift);
+  cudaFree(im->d_scratch);
   delete im;
   *impl = nullptr;
 }
@@ -1180,8 +1235,55 @@ int tc_conv_plan(TcConvPlan* plan, int B, int H, int W, int Cin, int Cout, int s
   plan->enabled = false;
   if (!tc_conv_eligible(Cin, Cout, size, stride, padding, y_cstride, y_coff)) return 0;
   TcImpl* im = new TcImpl();
-  std::vector<ConvGroup> groups = {{size, Cout, y_coff, 0}};
-  int rc = plan_common(im, B, H, W, Cin, groups, relu, has_affine, y_cstride, x_dev, y_dev, pool);
+  // Split-K for 3x3 convs whose item count leaves the last round of the persistent grid mostly
+  // idle (SqueezeDet's ConvDet head: 300 items on 148 SMs = 3 rounds for 2.03 rounds of work):
+  // three partial convs over the filter rows, then a deterministic reduction.
+  int ksplit = 1;
+  {
+    static int env_split = -1;
+    if (env_split < 0) {
+      const char* a = getenv("SQDET_TC_SPLITK");
+      env_split = a ? atoi(a) : 1;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ntiles = (long long)B * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W);
+    const bool few_items = Cout <= MAX_N && ntiles < 4LL * sms && (ntiles % sms) != 0 &&
+                           (double)(ntiles % sms) / sms < 0.5;
+    if (env_split && !pool && size == 3 && few_items && Cin >= 96 && (Cout % 4) == 0) ksplit = 3;
+  }
+  std::vector<ConvGroup> groups;
+  int rc;
+  if (ksplit == 1) {
+    groups = {{size, Cout, y_coff, 0}};
+    rc = plan_common(im, B, H, W, Cin, groups, relu, has_affine, y_cstride, x_dev, y_dev, pool);
+  } else {
+    const int pitch = (Cout + 7) / 8 * 8;
+    im->ksplit = ksplit;
+    im->pitch = pitch;
+    im->relu_final = relu;
+    im->cout = Cout;
+    im->y_cstride_final = y_cstride;
+    im->y_coff_final = y_coff;
+    im->npix = (long long)B * H * W;
+    im->y_final = y_dev;
+    cudaError_t ce = cudaMalloc(&im->d_scratch, sizeof(float) * (size_t)im->npix * ksplit * pitch);
+    if (ce != cudaSuccess) {
+      delete im;
+      return cuda_fail(ce, "cudaMalloc(split-K scratch)");
+    }
+    for (int s2 = 0; s2 < ksplit; ++s2) {
+      ConvGroup g{size, Cout, s2 * pitch, 0};
+      g.tap_begin = s2 * size;           // one filter row per partial
+      g.tap_count = size;
+      groups.push_back(g);
+    }
+    // partials: no bias / affine / relu in the conv epilogue (they are applied by the reduction)
+    rc = plan_common(im, B, H, W, Cin, groups, 0, has_affine, ksplit * pitch, x_dev, im->d_scratch,
+                     nullptr);
+    if (rc > 0) im->prm.bias = nullptr, im->prm.scale = nullptr, im->prm.shift = nullptr;
+  }
   if (rc <= 0) {
     void* p = im;
     release_impl(&p);
@@ -1191,6 +1293,7 @@ int tc_conv_plan(TcConvPlan* plan, int B, int H, int W, int Cin, int Cout, int s
   plan->B = B; plan->H = H; plan->W = W; plan->Cin = Cin; plan->Cout = Cout;
   plan->size = size; plan->stride = stride; plan->relu = relu; plan->Ho = H; plan->Wo = W;
   plan->y_cstride = y_cstride; plan->y_coff = y_coff;
+  plan->launches = im->ksplit > 1 ? 2 : 1;
   plan->impl = im;
   return 1;
 }
@@ -1216,7 +1319,7 @@ int tc_fire_plan(TcFirePlan* plan, int B, int H, int W, int S, int E1, int E3, c
 int tc_conv_pack_weights(TcConvPlan* plan, const float* w_hwio, const float* bias) {
   TcImpl* im = static_cast<TcImpl*>(plan->impl);
   std::vector<float> packed((size_t)im->rows_half * 2 * im->KC, 0.f);
-  pack_group(im, 0, w_hwio, packed);
+  for (int gi = 0; gi < (int)im->groups.size(); ++gi) pack_group(im, gi, w_hwio, packed);
   SQ_CUDA(cudaMemcpy(im->d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (bias)
     SQ_CUDA(cudaMemcpy(im->d_bias, bias, sizeof(float) * plan->Cout, cudaMemcpyHostToDevice));

@@ -11,6 +11,7 @@ struct TcConvPlan {
   int B = 0, H = 0, W = 0, Cin = 0, Cout = 0, size = 1, stride = 1, relu = 1;
   int Ho = 0, Wo = 0, pad_t = 0, pad_l = 0;
   int y_cstride = 0, y_coff = 0;
+  int launches = 1;              // 2 when the conv runs as split-K partials + reduction
   void* impl = nullptr;          // opaque device/host state (tensor maps, packed weights)
 };
 

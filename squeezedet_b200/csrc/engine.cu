@@ -790,7 +790,7 @@ int sqdet_finalize(sqdet_engine* e) {
             return fail(SQDET_ERR_STATE, "pool fusion was promised but the fire plan declined");
         }
       }
-      if (op.kind == OP_CONV) op.launches = 1;
+      if (op.kind == OP_CONV) op.launches = op.convs[0].tc.enabled ? op.convs[0].tc.launches : 1;
       else op.launches = 1 + (op.tcfire.enabled ? 1 : 2);
     } else if (op.kind == OP_POOL) {
       bytes = op.skip ? 0 : 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.dst].numel();
