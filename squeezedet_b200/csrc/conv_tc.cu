@@ -63,6 +63,9 @@ constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;   // 128 pixels
 constexpr int NUM_THREADS = 512;       // 4 warpgroups: {TMA, MMA, 2 spare} | splitter | drain A | drain B
 constexpr int MAX_CHUNKS = 16;
 constexpr int MAX_N = 128;          // output channels per item (register-resident running sums)
+constexpr int POOL_MAX_N = 64;      // ... when a max-pool is fused (conv tile staged per drain group)
+constexpr int POOL_MAX_GROUPS = POOL_MAX_N / 32;
+constexpr int POOL_STAGE_BYTES = POOL_MAX_GROUPS * (16384 + 4096);   // conv + pooled tiles
 constexpr int MAX_STAGES = 8;
 
 struct TcChunk {
@@ -98,6 +101,7 @@ struct TcParams {
   int ct_h, ct_w, step_h, step_w, org_h, org_w;   // origin = tile*step - org
   // fused max-pool (0 = none, else window 2 or 3; stride 2): pooled tile pt_h x pt_w, pooled dims
   int pool, pt_h, pt_w, Hp, Wp;
+  int store_ring;       // per-warp TMA-store staging tiles (2, or 1 to buy one more pipeline stage)
   int cluster;          // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast across it
   int exp_mode;         // timing experiments only (SQDET_TC_EXP): 1 no fence, 2 no store, 4 no STS
   long long* dbg;       // optional per-CTA cycle counters (SQDET_TC_DEBUG=1), else null
@@ -457,7 +461,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
         const TcChunk ck = p.chunk[item / spc];
         const int iters = ck.tap_count * p.kch;
-        const int owner = p.pool ? 0 : (n_item & 1);      // drain group of this item
+        const int owner = n_item & 1;                     // drain group of this item
         for (int i0 = 0; i0 < iters; i0 += G, ++g) {
           const int buf = g & 1;
           SQ_TIMED_WAIT(w_tempty, &tempty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);   // buffer drained
@@ -549,10 +553,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   } else {
     // ============================ segment drain + epilogue ================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-    // two drain groups (warps 8-11 and 12-15) take alternate items; the fused-pool epilogue
-    // needs a CTA-sized staging area, so there group 0 takes every item
+    // two drain groups (warps 8-11 and 12-15) take alternate items
     const int dgroup = (warp >= 12) ? 1 : 0;
-    const int ngroups = p.pool ? 1 : 2;
+    const int ngroups = 2;
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                 // accumulator row = pixel within the tile
     const int tt = threadIdx.x - 256 - 128 * dgroup;   // 0..127 within the drain group
@@ -564,7 +567,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
       const TcChunk ck = p.chunk[item / spc];
       const int iters = ck.tap_count * p.kch;
-      if ((n_item % ngroups) != dgroup || (p.pool && dgroup == 1)) {
+      if ((n_item % ngroups) != dgroup) {
         g += (iters + G - 1) / G;                // segments of an item the other group drains
         continue;
       }
@@ -629,11 +632,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             if (jg * 32 < ck.ch_count) {                  // warp-uniform
               if (lane == 0) {
                 const long long t0 = p.dbg ? clock64() : 0;
-                tma_store_wait_read_le1();                // the tile used 2 stores ago is free
+                if (p.store_ring == 2) tma_store_wait_read_le1();   // tile used 2 stores ago is free
+                else tma_store_wait_read_all();
                 if (p.dbg) c_stw += clock64() - t0;
               }
               __syncwarp();
-              uint8_t* tile_w = s_out + (dgroup * 4 + q) * 8192 + (n_store & 1) * 4096;
+              uint8_t* tile_w = s_out + (dgroup * 4 + q) * (4096 * p.store_ring) +
+                                (p.store_ring == 2 ? (n_store & 1) * 4096 : 0);
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int c = jg * 32 + k * 4;
@@ -672,7 +677,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int jg = 0; jg < MAX_N / 32; ++jg) {
             if (jg * 32 < ck.ch_count) {
-              uint8_t* tile_c = s_out + jg * 16384;
+              uint8_t* tile_c = s_out + dgroup * POOL_STAGE_BYTES + jg * 16384;
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int c = jg * 32 + k * 4;
@@ -700,13 +705,14 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           // unit = (channel group jg, pooled pixel pp, 16-byte chunk k2); pt_w == 8
           const int n_pp = p.pt_h * 8;
           const int n_units = ((ck.ch_count + 31) >> 5) * n_pp * 8;
-          uint8_t* pool_base = s_out + (MAX_N / 32) * 16384;
+          const uint8_t* conv_base = s_out + dgroup * POOL_STAGE_BYTES;
+          uint8_t* pool_base = s_out + dgroup * POOL_STAGE_BYTES + POOL_MAX_GROUPS * 16384;
           if (p.pool == 3) {
             for (int u = tt; u < n_units; u += 128)
-              pool_unit<3>(s_out, pool_base, u, n_pp);
+              pool_unit<3>(conv_base, pool_base, u, n_pp);
           } else {
             for (int u = tt; u < n_units; u += 128)
-              pool_unit<2>(s_out, pool_base, u, n_pp);
+              pool_unit<2>(conv_base, pool_base, u, n_pp);
           }
           if (p.dbg) c_pool += clock64() - tp0;
           fence_async_proxy();
@@ -919,7 +925,8 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   for (auto& g : groups) maxc = g.Cout > maxc ? g.Cout : maxc;
   int N = 0;
   {
-    const int nsplit = (maxc + MAX_N - 1) / MAX_N;
+    const int nmax = (pool && pool->size > 0) ? POOL_MAX_N : MAX_N;
+    const int nsplit = (maxc + nmax - 1) / nmax;
     N = ((maxc + nsplit - 1) / nsplit + 15) / 16 * 16;
   }
   TcParams& P = im->prm;
@@ -988,8 +995,23 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     const char* c = getenv("SQDET_TC_SEG");    env_seg = c ? atoi(c) : 0;
   }
   int ctas = env_ctas > 0 ? env_ctas : 1;   // 384 threads x 168 regs: one CTA per SM
-  const size_t overhead = 1024 /*alignment*/ + 512 /*barriers*/ + 4 * 3 * MAX_N * 4 /*epilogue params*/ +
-                          1024 + (pooled ? (MAX_N / 32) * (16384 + 4096) : 8 * 8192) /*store staging*/;
+  static int env_ring = -1;
+  if (env_ring < 0) {
+    const char* a = getenv("SQDET_TC_STORE_RING");
+    env_ring = a ? atoi(a) : 0;
+  }
+  auto overhead_for = [&](int ring) {
+    return (size_t)(1024 /*alignment*/ + 512 /*barriers*/ + 4 * 3 * MAX_N * 4 /*epilogue params*/ +
+                    1024 + (pooled ? 2 * POOL_STAGE_BYTES : 8 * 4096 * ring) /*store staging*/);
+  };
+  int ring = 2;
+  {
+    const size_t budget = 227 * 1024;
+    const int s2 = (int)((budget - overhead_for(2)) / stage), s1 = (int)((budget - overhead_for(1)) / stage);
+    if (env_ring == 1 || (env_ring == 0 && s2 < 4 && s1 > s2)) ring = 1;
+  }
+  P.store_ring = ring;
+  const size_t overhead = overhead_for(ring);
   int stages = 0;
   for (; ctas >= 1; --ctas) {
     const size_t budget = (ctas == 1 ? 227 * 1024 : (227 * 1024) / ctas - 1024) - overhead;
@@ -1217,7 +1239,7 @@ bool tc_pool_fusable(const int* couts, const int* coffs, int ngroups, int y_cstr
   if ((pool_size != 2 && pool_size != 3) || pool_stride != 2 || (y_cstride % 4)) return false;
   int maxc = 0;
   for (int g = 0; g < ngroups; ++g) maxc = couts[g] > maxc ? couts[g] : maxc;
-  const int nsplit = (maxc + MAX_N - 1) / MAX_N;
+  const int nsplit = (maxc + POOL_MAX_N - 1) / POOL_MAX_N;
   const int N = ((maxc + nsplit - 1) / nsplit + 15) / 16 * 16;
   int nchunks = 0;
   for (int g = 0; g < ngroups; ++g)
