@@ -102,6 +102,8 @@ struct TcParams {
   // fused max-pool (0 = none, else window 2 or 3; stride 2): pooled tile pt_h x pt_w, pooled dims
   int pool, pt_h, pt_w, Hp, Wp;
   int store_ring;       // per-warp TMA-store staging tiles (2, or 1 to buy one more pipeline stage)
+  int ablate;           // profiling builds only (-DSQDET_ABLATE): bitmask of pipeline pieces to skip
+  int two_cta;          // 1: CTA-pair MMA (cta_group::2), implies cluster == 2
   int cluster;          // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast across it
   int exp_mode;         // timing experiments only (SQDET_TC_EXP): 1 no fence, 2 no store, 4 no STS
   long long* dbg;       // optional per-CTA cycle counters (SQDET_TC_DEBUG=1), else null
@@ -213,6 +215,49 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
       "[%0], %1;" ::"r"(smem_u32(bar)),
       "h"(mask)
+      : "memory");
+}
+// ---- cta_group::2 (CTA-pair MMA): each CTA holds 128 rows of A in its own TMEM and HALF of
+// the B tile (N/2 rows) in its own smem; the leader CTA issues one M=256 MMA for the pair, so
+// the per-SM B smem traffic (reads and TMA fills) halves.
+__device__ __forceinline__ void tmem_alloc_2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2(uint64_t* bar) {   // arrives in BOTH CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(cta)
       : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -333,14 +378,15 @@ __device__ __forceinline__ float rn_tf32(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int KC>
+template <int KC, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~uintptr_t(1023));
   constexpr int A_BYTES = TILE_M * KC * 4;
-  const int B_BYTES = p.N * KC * 4;
+  // B tile bytes held by THIS CTA: all N rows, or N/2 in CTA-pair mode
+  const int B_BYTES = (TWO ? p.N / 2 : p.N) * KC * 4;
   const int STAGE_BYTES = A_BYTES + 2 * B_BYTES;   // [A raw][B hi][B lo]
   const int S = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * STAGE_BYTES);
@@ -373,16 +419,19 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&split[s], 128);
-      mbar_init(&empty[s], (uint32_t)C);     // one tcgen05.commit arrival from every CTA
+      mbar_init(&split[s], TWO ? 256 : 128);  // pair mode: both CTAs' splitters arrive at the leader
+      mbar_init(&empty[s], TWO ? 1u : (uint32_t)C);   // commit arrivals (pair mode: one multicast)
     }
     for (int b = 0; b < 4; ++b) mbar_init(&tfull[b], 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tempty[b], 128);
+      mbar_init(&tempty[b], TWO ? 256 : 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (TWO) tmem_alloc_2(tmem_slot, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
   if (C > 1) cluster_sync_all();           // peers' barriers exist before anyone multicasts
@@ -418,13 +467,29 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           if (++st_i == S) { st_i = 0; st_ph ^= 1u; }
           SQ_TIMED_WAIT(w_empty, &empty[s], ph ^ 1u);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+#ifdef SQDET_ABLATE
+          mbar_expect_tx(&full[s], ((p.ablate & 4) ? 0u : a_bytes) +
+                                       ((p.ablate & 2) ? 0u : (uint32_t)(2 * B_BYTES)));
+#else
           mbar_expect_tx(&full[s], a_bytes + (uint32_t)(2 * B_BYTES));
+#endif
           const int tl = i / p.kch, kc = i - tl * p.kch;
           const int tap = ck.tap_begin + tl;
           const int dy = tap / ck.ksize, dx = tap - dy * ck.ksize;
+#ifdef SQDET_ABLATE
+          if (!(p.ablate & 4))
+#endif
           tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
           const int row = ck.w_row_base + i * p.N;
-          if (C == 1) {
+#ifdef SQDET_ABLATE
+          if (p.ablate & 2) continue;
+#endif
+          if (TWO) {
+            // this CTA's half (rows crank*N/2 ...) of the hi and of the lo tile
+            const int r0 = (int)crank * (p.N / 2);
+            tma_load_2d(st + A_BYTES, &p.tmWs, &full[s], 0, row + r0);
+            tma_load_2d(st + A_BYTES + B_BYTES, &p.tmWs, &full[s], 0, row + r0 + p.lo_row_offset);
+          } else if (C == 1) {
             tma_load_2d(st + A_BYTES, &p.tmW, &full[s], 0, row);
             tma_load_2d(st + A_BYTES + B_BYTES, &p.tmW, &full[s], 0, row + p.lo_row_offset);
           } else {
@@ -447,10 +512,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
    } else if (warp == 1) {
     // ================================ MMA issuer =========================================
     // The whole warp walks the loop (warp-uniform addresses/descriptors live in uniform
-    // registers); only lane 0 issues tcgen05.mma / tcgen05.commit.
-    {
+    // registers); only lane 0 issues tcgen05.mma / tcgen05.commit.  In CTA-pair mode only the
+    // leader CTA (cluster rank 0) issues, for both CTAs.
+    if (!TWO || crank == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) |
-                             ((uint32_t)(TILE_M >> 4) << 24);
+                             ((uint32_t)((TWO ? 2 * TILE_M : TILE_M) >> 4) << 24);
       const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
       const uint64_t desc_hi = make_desc<KC>(0) & 0xFFFFFFFF00000000ull;   // layout/SBO/version
@@ -486,16 +552,29 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               for (int j = 0; j < KC / 8; ++j) {
                 const uint64_t dbh = desc_hi | (uint64_t)(b_hi + 2 * j);
                 const uint64_t dbl = desc_hi | (uint64_t)(b_lo + 2 * j);
-                umma_tf32_ts(d_tmem, a_lo + 8 * j, dbh, idesc, (i != i0 || j != 0) ? 1u : 0u);
-                umma_tf32_ts(d_tmem, a_hi + 8 * j, dbl, idesc, 1u);
-                umma_tf32_ts(d_tmem, a_hi + 8 * j, dbh, idesc, 1u);
+                if (TWO) {
+                  umma_tf32_ts_2(d_tmem, a_lo + 8 * j, dbh, idesc, (i != i0 || j != 0) ? 1u : 0u);
+                  umma_tf32_ts_2(d_tmem, a_hi + 8 * j, dbl, idesc, 1u);
+                  umma_tf32_ts_2(d_tmem, a_hi + 8 * j, dbh, idesc, 1u);
+                } else {
+                  umma_tf32_ts(d_tmem, a_lo + 8 * j, dbh, idesc, (i != i0 || j != 0) ? 1u : 0u);
+#ifdef SQDET_ABLATE
+                  if (p.ablate & 32) continue;
+#endif
+                  umma_tf32_ts(d_tmem, a_hi + 8 * j, dbl, idesc, 1u);
+                  umma_tf32_ts(d_tmem, a_hi + 8 * j, dbh, idesc, 1u);
+                }
               }
-              if (C == 1) umma_commit(&empty[s]);   // frees the smem stage once the MMAs read it
+              if (TWO) umma_commit_2(&empty[s]);    // frees the stage in both CTAs of the pair
+              else if (C == 1) umma_commit(&empty[s]);   // frees the smem stage once the MMAs read it
               else umma_commit_mc(&empty[s], cmask);   // ... in every CTA of the cluster
             }
             __syncwarp();
           }
-          if (elect_one()) umma_commit(&tfull[owner * 2 + buf]);   // segment complete -> its drain group
+          if (elect_one()) {                       // segment complete -> its drain group
+            if (TWO) umma_commit_2(&tfull[owner * 2 + buf]);
+            else umma_commit(&tfull[owner * 2 + buf]);
+          }
           __syncwarp();
         }
       }
@@ -526,6 +605,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const int sw = (KC == 32) ? (t & 7) : ((t >> 1) & 3);
         const uint32_t a_slot = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
                                 (uint32_t)(2 * p.N + s * 2 * KC);
+#ifdef SQDET_ABLATE
+        if (!(p.ablate & 1))
+#endif
 #pragma unroll
         for (int hblk = 0; hblk < KC / 16; ++hblk) {       // 16 columns at a time
           uint32_t hi[16], lo[16];
@@ -536,9 +618,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+              // a = h + l exactly (h: 11-bit RN of a, l = a - h fits fp32); the tensor core
+              // reads the top 19 bits of l, i.e. |l| * 2^-10 <= 2^-21 |a| is dropped
               const float h = rn_tf32(vv[e]);
               hi[k * 4 + e] = __float_as_uint(h);
-              lo[k * 4 + e] = __float_as_uint(rn_tf32(vv[e] - h));
+              lo[k * 4 + e] = __float_as_uint(vv[e] - h);
             }
           }
           tmem_st16(a_slot + (uint32_t)(hblk * 16), hi);
@@ -546,7 +630,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         }
         tmem_wait_st();
         tc_fence_before();             // order the TMEM writes before the barrier hand-off
-        mbar_arrive(&split[s]);
+        if (TWO) mbar_arrive_remote(&split[s], 0u);   // the leader CTA's barrier
+        else mbar_arrive(&split[s]);
       }
     }
     if (p.dbg && t == 0) p.dbg[blockIdx.x * 12 + 3] = w_full;
@@ -563,7 +648,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     int g = 0;
     long long w_tfull = 0, c_epi = 0, c_stw = 0, c_pool = 0, c_par = 0;
     int n_item = 0, n_own = 0, n_store = 0;
-    uint32_t use[2] = {0u, 0u};                  // own segments seen per TMEM buffer
+    uint32_t use0 = 0u, use1 = 0u;               // own segments seen per TMEM buffer
     for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
       const TcChunk ck = p.chunk[item / spc];
       const int iters = ck.tap_count * p.kch;
@@ -595,10 +680,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       ++n_own;
       for (int i0 = 0; i0 < iters; i0 += G, ++g) {
         const int buf = g & 1;
-        SQ_TIMED_WAIT(w_tfull, &tfull[dgroup * 2 + buf], use[buf] & 1u);
-        ++use[buf];
+        SQ_TIMED_WAIT(w_tfull, &tfull[dgroup * 2 + buf], (buf ? use1 : use0) & 1u);
+        if (buf) ++use1; else ++use0;
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.N);
+#ifdef SQDET_ABLATE
+        if (!(p.ablate & 8))
+#endif
 #pragma unroll
         for (int c0 = 0; c0 < MAX_N; c0 += 16) {
           if (c0 < ncols) {                      // warp-uniform
@@ -611,13 +699,17 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           }
         }
         tc_fence_before();
-        mbar_arrive(&tempty[buf]);               // buffer may be overwritten by segment g+2
+        if (TWO) mbar_arrive_remote(&tempty[buf], 0u);
+        else mbar_arrive(&tempty[buf]);          // buffer may be overwritten by segment g+2
       }
       // ---- epilogue: bias [, affine], relu, 128-bit stores of this pixel's channel run ----
       const long long t_epi = p.dbg ? clock64() : 0;
       const int r_h = r / p.ct_w, r_w = r - r_h * p.ct_w;
       const int oh = h0 + r_h, ow = w0 + r_w;
       const bool pix_ok = (r_h < p.ct_h) && oh >= 0 && ow >= 0 && oh < p.Ho && ow < p.Wo;
+#ifdef SQDET_ABLATE
+      if (p.ablate & 16) continue;
+#endif
       if (p.tma_store) {
         // TMEM-drained sums -> (+bias [*scale+shift], relu) -> swizzled smem tiles -> TMA
         // stores.  The TMA unit writes whole 128-byte lines asynchronously and clips ragged
@@ -781,7 +873,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   if (C > 1) cluster_sync_all();           // no CTA leaves while peers may still multicast to it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (TWO) tmem_dealloc_2(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -978,14 +1071,24 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   P.N = N;
 
   // ~24 chained MMAs per accumulation segment (3 MMAs per 8-wide K step)
-  P.seg_stages = (KC == 32) ? 2 : 4;
+  // 48 chained MMAs per accumulation segment: measured relative error 7e-7 (24: 4e-7, 96: 1.3e-6;
+  // fp32 SIMT accumulation: 1e-6 .. 2e-6) and 5% faster end to end than 24
+  P.seg_stages = (KC == 32) ? 4 : 8;
   P.ntiles = B * P.tiles_h * P.tiles_w;
   P.y_cstride = y_cstride;
   P.relu = relu;
   P.lo_row_offset = row;
   P.nchunks = (int)im->chunks.size();
   for (int i = 0; i < P.nchunks; ++i) P.chunk[i] = im->chunks[i];
-  const size_t stage = (size_t)TILE_M * KC * 4 + (size_t)2 * N * KC * 4;
+  // CTA-pair mode (cta_group::2): needs N % 32 == 0 (2-SM TF32 MMA shape rule) and two tiles
+  static int env_two = -1;
+  if (env_two < 0) {
+    const char* a = getenv("SQDET_TC_2CTA");
+    env_two = a ? atoi(a) : 0;
+  }
+  const bool two_cta = env_two != 0 && (N % 32 == 0) && P.ntiles >= 2;
+  P.two_cta = two_cta ? 1 : 0;
+  const size_t stage = (size_t)TILE_M * KC * 4 + (size_t)2 * (two_cta ? N / 2 : N) * KC * 4;
   // Pipeline depth and residency: with two CTAs per SM (<= ~110 KB each) there are two
   // independent TMA->split->MMA->drain pipelines per SM to hide latency; otherwise one deep one.
   static int env_ctas = -1, env_stages = -1, env_seg = -1;
@@ -1032,6 +1135,10 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     P.tmem_cols = cols;
   }
   if (env_seg > 0) P.seg_stages = env_seg;
+  {
+    const char* a = getenv("SQDET_TC_ABLATE");
+    P.ablate = a ? atoi(a) : 0;
+  }
   im->smem_bytes = stages * stage + overhead;
   {
     int dev = 0, sms = 148;
@@ -1045,6 +1152,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
       env_cluster = a ? atoi(a) : 1;   // measured: multicast (2, 4) is slower, see DESIGN.md
     }
     int cluster = (env_cluster == 4 || env_cluster == 2) ? env_cluster : 1;
+    if (P.two_cta) cluster = 2;
     if (P.ntiles < cluster) cluster = 1;
     P.cluster = cluster;
     const long long supers = (long long)((P.ntiles + cluster - 1) / cluster) * P.nchunks;
@@ -1092,17 +1200,21 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   rc = encode_w_map(&P.tmW, im->d_w, row * 2, KC, N);
   if (rc) return rc;
   if (P.cluster > 1) {
-    rc = encode_w_map(&P.tmWs, im->d_w, row * 2, KC, 2 * N / P.cluster);
+    rc = encode_w_map(&P.tmWs, im->d_w, row * 2, KC, P.two_cta ? N / 2 : 2 * N / P.cluster);
     if (rc) return rc;
   }
   // opt in to the full 227 KB once for both instantiations (the attribute is per function,
   // not per launch, so it must cover the largest plan)
   static bool attr_set = false;
   if (!attr_set) {
-    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 232448));
-    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 232448));
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   return 1;
@@ -1161,9 +1273,9 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
   if (prm.cluster <= 1) {
     // classic launch (no cluster attribute: keeps the non-cluster CTA->SM placement path)
     if (im->KC == 32)
-      conv_tc_kernel<32><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+      conv_tc_kernel<32, false><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
     else
-      conv_tc_kernel<16><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+      conv_tc_kernel<16, false><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = im->grid;
@@ -1177,8 +1289,13 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = (im->KC == 32) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<32>, prm)
-                                    : cudaLaunchKernelEx(&cfg, conv_tc_kernel<16>, prm);
+    cudaError_t le;
+    if (prm.two_cta)
+      le = (im->KC == 32) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, true>, prm)
+                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true>, prm);
+    else
+      le = (im->KC == 32) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, false>, prm)
+                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false>, prm);
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(conv_tc_kernel)");
   }
   SQ_CHECK_LAUNCH("conv_tc_kernel");
@@ -1200,10 +1317,10 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     for (int b = 0; b < nb; ++b)
       for (int k = 0; k < 12; ++k) a[k] += (double)h[(size_t)b * 12 + k] / nb;
     fprintf(stderr,
-            "[tc] grid %d cluster %d smem %zu KC %d N %d kch %d chunks %d stages %d seg %d | per-CTA avg cycles: "
+            "[tc] grid %d cluster %d%s smem %zu KC %d N %d kch %d chunks %d stages %d seg %d | per-CTA avg cycles: "
             "total %.0f stages %.0f | waits: producer(empty) %.0f mma(split) %.0f mma(tempty) %.0f "
             "splitter(full) %.0f drain(tfull) %.0f | epilogue %.0f (store-wait %.0f, pool %.0f, params %.0f)\n",
-            nb, prm.cluster, im->smem_bytes, im->KC, prm.N, prm.kch, prm.nchunks, prm.stages, prm.seg_stages,
+            nb, prm.cluster, prm.two_cta ? " (cta_group::2)" : "", im->smem_bytes, im->KC, prm.N, prm.kch, prm.nchunks, prm.stages, prm.seg_stages,
             a[5], a[6], a[0], a[1], a[2], a[3], a[4], a[7], a[8], a[9], a[10]);
   }
   return SQDET_OK;
