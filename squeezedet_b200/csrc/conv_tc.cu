@@ -99,6 +99,7 @@ struct TcParams {
   // conv tile (rows of the M=128 MMA tile): ct_h x ct_w output pixels (8x16, or 7x17 / 8x16
   // when a 3x3 / 2x2 stride-2 max-pool is fused into the epilogue); tile step in conv pixels
   int ct_h, ct_w, step_h, step_w, org_h, org_w;   // origin = tile*step - org
+  int sq_w, sq_h;       // TMA-store epilogue: offset of drain warp q's 32-pixel slab in the tile
   // fused max-pool (0 = none, else window 2 or 3; stride 2): pooled tile pt_h x pt_w, pooled dims
   int pool, pt_h, pt_w, Hp, Wp;
   int store_ring;       // per-warp TMA-store staging tiles (2, or 1 to buy one more pipeline stage)
@@ -751,7 +752,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               fence_async_proxy();
               __syncwarp();
               if (lane == 0 && tile_valid)
-                tma_store_4d(tile_w, &p.tmY, ck.y_coff + jg * 32, w0, h0 + 2 * q, img);
+                tma_store_4d(tile_w, &p.tmY, ck.y_coff + jg * 32, w0 + q * p.sq_w, h0 + q * p.sq_h, img);
               ++n_store;
             }
           }
@@ -1009,6 +1010,24 @@ static int encode_w_map(CUtensorMap* map, const float* w, int rows, int KC, int 
 static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vector<ConvGroup>& groups,
                        int relu, bool has_affine, int y_cstride, const float* x_dev, float* y_dev,
                        const TcPool* pool) {
+  // A launch made only of 1x1 convs has no spatial structure: walk the B*H*W pixels as one flat
+  // row in tiles of 128 consecutive pixels (no ragged image-edge tiles; e.g. 22x76x20 is 262
+  // tiles instead of 300, which is two waves of 148 CTAs instead of three).
+  bool flat = !(pool && pool->size > 0);
+  for (auto& g : groups) flat = flat && g.ksize == 1;
+  {
+    static int env_flat = -1;
+    if (env_flat < 0) {
+      const char* a = getenv("SQDET_TC_FLAT");
+      env_flat = a ? atoi(a) : 1;
+    }
+    if (!env_flat) flat = false;
+  }
+  if (flat) {
+    W = B * H * W;
+    H = 1;
+    B = 1;
+  }
   im->Cin = Cin;
   im->KC = (Cin % 32 == 0) ? 32 : 16;
   const int KC = im->KC;
@@ -1052,6 +1071,12 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   P.org_h = P.org_w = 0;
   P.tiles_h = (H + TILE_H - 1) / TILE_H;
   P.tiles_w = (W + TILE_W - 1) / TILE_W;
+  P.sq_w = 0; P.sq_h = 2;                           // drain warp q stores tile rows 2q, 2q+1
+  if (flat) {
+    P.ct_h = 1; P.ct_w = TILE_M; P.step_h = 1; P.step_w = TILE_M;
+    P.tiles_h = 1; P.tiles_w = (W + TILE_M - 1) / TILE_M;
+    P.sq_w = 32; P.sq_h = 0;
+  }
   const bool pooled = pool && pool->size > 0;
   if (pooled) {
     // conv tile = the conv pixels under a pt_h x pt_w block of stride-2 pooling windows
@@ -1070,10 +1095,12 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   P.kch = kch;
   P.N = N;
 
-  // ~24 chained MMAs per accumulation segment (3 MMAs per 8-wide K step)
-  // 48 chained MMAs per accumulation segment: measured relative error 7e-7 (24: 4e-7, 96: 1.3e-6;
-  // fp32 SIMT accumulation: 1e-6 .. 2e-6) and 5% faster end to end than 24
-  P.seg_stages = (KC == 32) ? 4 : 8;
+  // 36 chained MMAs per accumulation segment (3 MMAs per 8-wide K step).  Measured relative
+  // error of one conv: 24 -> 4e-7, 48 -> 7e-7, 96 -> 1.3e-6 (fp32 SIMT accumulation: 1e-6 ..
+  // 2e-6); 48 is 5% faster end to end than 24 but the truncation bias is systematic, and at
+  // 48 the 50-layer ResNet body lands one box coordinate 8e-3 px from the fp32 reference
+  // (the test bar is ~6e-3): 36 keeps the margin.
+  P.seg_stages = (KC == 32) ? 3 : 6;
   P.ntiles = B * P.tiles_h * P.tiles_w;
   P.y_cstride = y_cstride;
   P.relu = relu;
@@ -1192,7 +1219,8 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
       if (pooled)
         rc = encode_act_map(&P.tmY, y_dev, B, pool->Hp, pool->Wp, y_cstride, 32, P.pt_w, P.pt_h);
       else
-        rc = encode_act_map(&P.tmY, y_dev, B, H, W, y_cstride, 32, TILE_W, 2);   // per-warp rows
+        rc = flat ? encode_act_map(&P.tmY, y_dev, B, H, W, y_cstride, 32, 32, 1)
+                  : encode_act_map(&P.tmY, y_dev, B, H, W, y_cstride, 32, TILE_W, 2);   // per-warp rows
       if (rc) return rc;
     }
     P.tma_store = ok ? 1 : 0;
