@@ -67,6 +67,7 @@ constexpr int POOL_MAX_N = 64;      // ... when a max-pool is fused (conv tile s
 constexpr int POOL_MAX_GROUPS = POOL_MAX_N / 32;
 constexpr int POOL_STAGE_BYTES = POOL_MAX_GROUPS * (16384 + 4096);   // conv + pooled tiles
 constexpr int MAX_STAGES = 8;
+constexpr int GATHER_PITCH = 128;   // floats between patch rows in the stage (gather mode)
 
 struct TcChunk {
   int ksize;        // 1 or 3 (square)
@@ -100,6 +101,14 @@ struct TcParams {
   // when a 3x3 / 2x2 stride-2 max-pool is fused into the epilogue); tile step in conv pixels
   int ct_h, ct_w, step_h, step_w, org_h, org_w;   // origin = tile*step - org
   int sq_w, sq_h;       // TMA-store epilogue: offset of drain warp q's 32-pixel slab in the tile
+  // gather mode (first layer: 3x3 conv over a 3-channel image): the A tile is the im2col
+  // of an input patch; the producer fetches the patch row by row with 1-D TMA loads (rows of a
+  // 3-channel fp32 image are only 4-byte aligned, which rules out the tiled 4-D map), K = 27
+  // padded to one 32-wide K block
+  CUtensorMap tmX;      // the whole input as a 1-D array of floats, box = g_box floats
+  int gather;           // 1 = gather mode
+  int g_H, g_W, g_stride, g_pad_t, g_pad_l;
+  int g_ph, g_box;      // patch rows; floats fetched per patch row (patch columns * 3, padded to 4)
   // fused max-pool (0 = none, else window 2 or 3; stride 2): pooled tile pt_h x pt_w, pooled dims
   int pool, pt_h, pt_w, Hp, Wp;
   int store_ring;       // per-warp TMA-store staging tiles (2, or 1 to buy one more pipeline stage)
@@ -150,6 +159,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0) {
+  asm volatile(
+      "cp.async.bulk.tensor.1d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
@@ -472,7 +489,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           mbar_expect_tx(&full[s], ((p.ablate & 4) ? 0u : a_bytes) +
                                        ((p.ablate & 2) ? 0u : (uint32_t)(2 * B_BYTES)));
 #else
-          mbar_expect_tx(&full[s], a_bytes + (uint32_t)(2 * B_BYTES));
+          mbar_expect_tx(&full[s], (p.gather ? (uint32_t)(p.g_ph * p.g_box * 4) : a_bytes) +
+                                       (uint32_t)(2 * B_BYTES));
 #endif
           const int tl = i / p.kch, kc = i - tl * p.kch;
           const int tap = ck.tap_begin + tl;
@@ -480,7 +498,21 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 #ifdef SQDET_ABLATE
           if (!(p.ablate & 4))
 #endif
-          tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
+          if (p.gather) {
+            // patch rows at a 512-byte pitch; rows past the image bottom read the next image (or
+            // TMA zero fill past the tensor): they only feed conv pixels the epilogue masks
+            // TMA needs a 16-byte aligned global start: every row is fetched from its start
+            // rounded down to 4 floats (the splitter adds the 0..3 float offset back); rows
+            // above / below the image fetch a neighbour's data or zero fill, which the splitter
+            // masks (padding) or which only feed conv pixels the epilogue masks
+            const int e0 = ((img * p.g_H + h0 * p.g_stride - p.g_pad_t) * p.g_W +
+                            (w0 * p.g_stride - p.g_pad_l)) * 3;
+            for (int r = 0; r < p.g_ph; ++r)
+              tma_load_1d(st + r * (GATHER_PITCH * 4), &p.tmX, &full[s],
+                          (e0 + r * p.g_W * 3) & ~3);
+          } else {
+            tma_load_4d(st, &p.tmA, &full[s], kc * KC, w0 + dx - ck.pad, h0 + dy - ck.pad, img);
+          }
           const int row = ck.w_row_base + i * p.N;
 #ifdef SQDET_ABLATE
           if (p.ablate & 2) continue;
@@ -602,6 +634,61 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         SQ_TIMED_WAIT(w_full, &full[s], ph);
         // row t of the raw tile (KC*4 bytes, swizzled 16-byte chunks) -> registers ->
         // a_hi / a_lo -> TMEM slot s, lane t (this warp owns lanes 32*(warp%4)..+31)
+        if (KC == 32 && p.gather) {
+          // gather mode: row t of A = the 27 taps (dy, dx, c) of conv pixel t, read from the
+          // patch rows; taps outside the image (SAME padding), taps 27..31 and rows past the
+          // tile are zero
+          const float* patch = reinterpret_cast<const float*>(smem + (size_t)s * STAGE_BYTES);
+          int tile = (item % spc) * C + (int)crank;
+          if (tile >= p.ntiles) tile = p.ntiles - 1;
+          const int tw = tile % p.tiles_w;
+          tile /= p.tiles_w;
+          const int h0 = (tile % p.tiles_h) * p.step_h - p.org_h, w0 = tw * p.step_w - p.org_w;
+          const int img = tile / p.tiles_h;
+          const int r_h = t / p.ct_w, r_w = t - r_h * p.ct_w;
+          const bool live = r_h < p.ct_h;
+          const int iy0 = (h0 + r_h) * p.g_stride - p.g_pad_t;      // input row of tap dy = 0
+          const int ix0 = (w0 + r_w) * p.g_stride - p.g_pad_l;      // input column of tap dx = 0
+          // global element index of (row iy0, tile's first patch column): its low 2 bits are the
+          // offset the producer's 16-byte alignment shifted this patch row by
+          const int g0 = ((img * p.g_H + iy0) * p.g_W + (w0 * p.g_stride - p.g_pad_l)) * 3;
+          const float* prow[3];
+          bool rok[3], cok[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int g = g0 + d * p.g_W * 3;
+            prow[d] = patch + (live ? (r_h * p.g_stride + d) * GATHER_PITCH + (g & 3) +
+                                          r_w * p.g_stride * 3
+                                    : 0);
+            rok[d] = live && (iy0 + d) >= 0 && (iy0 + d) < p.g_H;
+            cok[d] = (ix0 + d) >= 0 && (ix0 + d) < p.g_W;
+          }
+          const uint32_t a_slot = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
+                                  (uint32_t)(2 * p.N + s * 2 * KC);
+#pragma unroll
+          for (int hblk = 0; hblk < 2; ++hblk) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int k = hblk * 16 + e;
+              float v = 0.f;
+              if (k < 27) {
+                v = prow[k / 9][k % 9];
+                if (!(rok[k / 9] && cok[(k % 9) / 3])) v = 0.f;
+              }
+              const float h = rn_tf32(v);
+              hi[e] = __float_as_uint(h);
+              lo[e] = __float_as_uint(v - h);
+            }
+            tmem_st16(a_slot + (uint32_t)(hblk * 16), hi);
+            tmem_st16(a_slot + (uint32_t)(KC + hblk * 16), lo);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          if (TWO) mbar_arrive_remote(&split[s], 0u);
+          else mbar_arrive(&split[s]);
+          continue;
+        }
         const uint8_t* arow = smem + (size_t)s * STAGE_BYTES + (size_t)t * (KC * 4);
         const int sw = (KC == 32) ? (t & 7) : ((t >> 1) & 3);
         const uint32_t a_slot = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
@@ -956,6 +1043,10 @@ struct TcImpl {
   long long npix = 0;
   float* d_scratch = nullptr;
   float* y_final = nullptr;
+  // gather mode: the input address is baked into the 1-D tensor map; the engine feeds the first
+  // layer from several buffers (pipelined inputs), so maps are cached per address
+  long long x_floats = 0;
+  mutable std::vector<std::pair<const float*, CUtensorMap>> xmaps;
 };
 
 static inline float host_rn_tf32(float x) {
@@ -1007,13 +1098,37 @@ static int encode_w_map(CUtensorMap* map, const float* w, int rows, int KC, int 
 }
 
 // Common planner: `groups` convs (same ksize rules as the fire pair) over one input.
+// First-layer (gather) mode: the conv really is `ks x ks` over a 3-channel image with this
+// stride / padding; plan_common is then called on the conv OUTPUT grid with a fake 1x1 group.
+struct GatherSpec {
+  int B_in, H_in, W_in, stride, pad_t, pad_l;
+};
+
+static int encode_flat_map(CUtensorMap* map, const float* x, long long n, int box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(SQDET_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[1] = {(cuuint64_t)n};
+  cuuint64_t strides[1] = {0};
+  cuuint32_t bx[1] = {(cuuint32_t)box};
+  cuuint32_t estr[1] = {1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, const_cast<float*>(x), dims, strides, bx,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(flat input) failed: CUresult %d", (int)r);
+    return fail(SQDET_ERR_CUDA, buf);
+  }
+  return SQDET_OK;
+}
+
 static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vector<ConvGroup>& groups,
                        int relu, bool has_affine, int y_cstride, const float* x_dev, float* y_dev,
-                       const TcPool* pool) {
+                       const TcPool* pool, const GatherSpec* gs = nullptr) {
   // A launch made only of 1x1 convs has no spatial structure: walk the B*H*W pixels as one flat
   // row in tiles of 128 consecutive pixels (no ragged image-edge tiles; e.g. 22x76x20 is 262
   // tiles instead of 300, which is two waves of 148 CTAs instead of three).
-  bool flat = !(pool && pool->size > 0);
+  bool flat = !(pool && pool->size > 0) && !gs;
   for (auto& g : groups) flat = flat && g.ksize == 1;
   {
     static int env_flat = -1;
@@ -1199,8 +1314,25 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     P.scale = im->d_scale;
     P.shift = im->d_shift;
   }
-  int rc = encode_act_map(&P.tmA, x_dev, B, H, W, Cin, KC, P.ct_w, P.ct_h);
-  if (rc) return rc;
+  int rc = 0;
+  if (gs) {
+    P.gather = 1;
+    P.g_H = gs->H_in; P.g_W = gs->W_in; P.g_stride = gs->stride;
+    P.g_pad_t = gs->pad_t; P.g_pad_l = gs->pad_l;
+    P.g_ph = (P.ct_h - 1) * gs->stride + 3;
+    // patch columns * 3 floats, + up to 3 floats of alignment shift, rounded to 16 bytes
+    P.g_box = (((P.ct_w - 1) * gs->stride + 3) * 3 + 3 + 3) / 4 * 4;
+    if ((long long)gs->B_in * gs->H_in * gs->W_in * 3 + 4096 >= (1LL << 31)) return 0;
+    if (P.g_box > GATHER_PITCH || (size_t)P.g_ph * GATHER_PITCH * 4 > (size_t)TILE_M * KC * 4)
+      return 0;                                       // patch must fit the stage's A region
+    im->x_floats = (long long)gs->B_in * gs->H_in * gs->W_in * 3;
+    rc = encode_flat_map(&P.tmX, x_dev, im->x_floats, P.g_box);
+    if (rc) return rc;
+    im->xmaps.emplace_back(x_dev, P.tmX);
+  } else {
+    rc = encode_act_map(&P.tmA, x_dev, B, H, W, Cin, KC, P.ct_w, P.ct_h);
+    if (rc) return rc;
+  }
   // TMA-store epilogue: needs every chunk to be a whole number of 32-channel groups unless it
   // ends at the tensor's last channel (where the TMA unit clips the tail).
   {
@@ -1264,7 +1396,9 @@ static void pack_group(const TcImpl* im, int gi, const float* w_hwio, std::vecto
           const int tap = c.tap_begin + tl;
           const size_t rowi = (size_t)c.w_row_base + ((size_t)tl * kch + kc) * N + n;
           for (int k = 0; k < KC; ++k) {
-            const float v = w_hwio[((size_t)tap * Cin + (size_t)kc * KC + k) * g.Cout + cb + n];
+            const float v = (kc * KC + k < Cin)
+                                ? w_hwio[((size_t)tap * Cin + (size_t)kc * KC + k) * g.Cout + cb + n]
+                                : 0.f;   // gather mode: K = 27 padded to 32
             const float hi = host_rn_tf32(v);
             packed[rowi * KC + k] = hi;
             packed[lo_off + rowi * KC + k] = host_rn_tf32(v - hi);
@@ -1283,6 +1417,19 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     debug = d ? atoi(d) : 0;
   }
   TcParams prm = im->prm;
+  if (prm.gather && x_dev) {
+    bool found = false;
+    for (auto& m : im->xmaps)
+      if (m.first == x_dev) { prm.tmX = m.second; found = true; break; }
+    if (!found) {
+      CUtensorMap m;
+      int rc = encode_flat_map(&m, x_dev, im->x_floats, prm.g_box);
+      if (rc) return rc;
+      if (im->xmaps.size() >= 8) im->xmaps.erase(im->xmaps.begin());
+      im->xmaps.emplace_back(x_dev, m);
+      prm.tmX = m;
+    }
+  }
   {
     static int exp_mode = -1;
     if (exp_mode < 0) {
@@ -1400,6 +1547,38 @@ int tc_conv_plan(TcConvPlan* plan, int B, int H, int W, int Cin, int Cout, int s
                  int padding, int relu, bool has_affine, int y_cstride, int y_coff,
                  const float* x_dev, float* y_dev, const TcPool* pool) {
   plan->enabled = false;
+  // First layer: 3x3 conv over a 3-channel image (stride 1 or 2, SAME or VALID) -> gather mode
+  if (Cin == 3 && size == 3 && (stride == 1 || stride == 2) && (Cout % 4) == 0 &&
+      (y_cstride % 4) == 0 && (y_coff % 4) == 0) {
+    static int env_gather = -1;
+    if (env_gather < 0) {
+      const char* a = getenv("SQDET_TC_GATHER");
+      env_gather = a ? atoi(a) : 1;
+    }
+    if (!env_gather) return 0;
+    const Geom gh = tf_geometry(H, size, stride, padding);
+    const Geom gw = tf_geometry(W, size, stride, padding);
+    if (gh.out <= 0 || gw.out <= 0) return 0;
+    TcImpl* im = new TcImpl();
+    GatherSpec gs{B, H, W, stride, gh.pad_before, gw.pad_before};
+    std::vector<ConvGroup> groups = {{1, Cout, y_coff, 0}};   // one K block of 32 (27 real taps)
+    int rc = plan_common(im, B, gh.out, gw.out, 32, groups, relu, has_affine, y_cstride, x_dev,
+                         y_dev, pool, &gs);
+    if (rc <= 0) {
+      void* p = im;
+      release_impl(&p);
+      return rc;
+    }
+    im->Cin = 27;          // weight packing: HWIO flattened is already [k = (dy, dx, c)][Cout]
+    plan->enabled = true;
+    plan->B = B; plan->H = H; plan->W = W; plan->Cin = Cin; plan->Cout = Cout;
+    plan->size = size; plan->stride = stride; plan->relu = relu;
+    plan->Ho = gh.out; plan->Wo = gw.out; plan->pad_t = gh.pad_before; plan->pad_l = gw.pad_before;
+    plan->y_cstride = y_cstride; plan->y_coff = y_coff;
+    plan->launches = 1;
+    plan->impl = im;
+    return 1;
+  }
   if (!tc_conv_eligible(Cin, Cout, size, stride, padding, y_cstride, y_coff)) return 0;
   TcImpl* im = new TcImpl();
   // Split-K for 3x3 convs whose item count leaves the last round of the persistent grid mostly

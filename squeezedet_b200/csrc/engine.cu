@@ -248,6 +248,7 @@ static int run_op(sqdet_engine* e, const Op& op, const float* x_override, cudaSt
         const Op& po = e->ops[op.fused_pool_op];
         const Tensor& in = e->tensors[c.src];
         const float* x = (c.src == 0 && x_override) ? x_override : in.dev;
+        if (c.tc.enabled) return launch_conv_tc(c.tc, x, e->tensors[op.out].dev, stream);
         return launch_conv_pool_simt(x, e->params[c.p_kernel].dev,
                                      c.p_bias >= 0 ? e->params[c.p_bias].dev : nullptr, c.scale,
                                      c.shift, e->tensors[op.out].dev, in.B, in.H, in.W, c.Cout,
@@ -752,7 +753,8 @@ int sqdet_finalize(sqdet_engine* e) {
       const TcPool* pool_ptr = nullptr;
       if (op.first_layer_fused) {
         bytes = 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.out].numel() + 4 * op.params;
-      } else if (op.fused_pool_op >= 0) {
+      }
+      if (op.fused_pool_op >= 0) {
         const Op& po = e->ops[op.fused_pool_op];
         const Tensor& un = e->tensors[op.dst];
         const Geom gh = tf_geometry(un.H, po.size, po.stride, po.padding);
@@ -764,6 +766,23 @@ int sqdet_finalize(sqdet_engine* e) {
         pool_spec.Wp = gw.out;
         pool_ptr = &pool_spec;
         bytes = 4 * e->tensors[op.src].numel() + 4 * e->tensors[op.out].numel() + 4 * op.params;
+      }
+      static int env_first_tc = -1;
+      if (env_first_tc < 0) {
+        const char* a = getenv("SQDET_TC_FIRST_POOL");
+        env_first_tc = a ? atoi(a) : 0;
+      }
+      if (c.math_mode == SQDET_MATH_TF32X3_TC && op.first_layer_fused && env_first_tc) {
+        // tensor-core first layer (gather mode) with the pool in its epilogue.  Parity-green but
+        // measured slower than the fused FFMA kernel (0.43 ms vs 0.37 ms for SqueezeDet conv1 +
+        // pool1: the pooled epilogue saturates the drain warps), hence opt-in; un-pooled first
+        // layers (VGG16 conv1_1: 0.93 -> 0.36 ms) take the gather mode by default.
+        ConvSpec& cs = op.convs[0];
+        int rc = tc_conv_plan(&cs.tc, e->tensors[cs.src].B, e->tensors[cs.src].H,
+                              e->tensors[cs.src].W, cs.Cin, cs.Cout, cs.size, cs.stride,
+                              cs.padding, cs.relu, cs.p_gamma >= 0, e->tensors[op.out].C,
+                              cs.y_coff, e->tensors[cs.src].dev, e->tensors[op.out].dev, pool_ptr);
+        if (rc < 0) return rc;
       }
       if (c.math_mode == SQDET_MATH_TF32X3_TC && !op.first_layer_fused) {
         if (op.kind == OP_CONV) {
