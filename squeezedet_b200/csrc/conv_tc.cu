@@ -51,6 +51,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <queue>
 #include <vector>
 
 #include "common.cuh"
@@ -116,6 +118,10 @@ struct TcParams {
   int two_cta;          // 1: CTA-pair MMA (cta_group::2), implies cluster == 2
   int cluster;          // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast across it
   int exp_mode;         // timing experiments only (SQDET_TC_EXP): 1 no fence, 2 no store, 4 no STS
+  // static schedule (launches whose chunks differ in cost): sched[0 .. nbins] = first entry of each
+  // cluster's item list, followed by the lists (longest-processing-time-first assignment);
+  // null = round-robin `item = cluster id + k * clusters`
+  const int* sched;
   long long* dbg;       // optional per-CTA cycle counters (SQDET_TC_DEBUG=1), else null
   int y_cstride, relu;
   int lo_row_offset;    // rows between the hi and the lo copy of the packed weights
@@ -396,7 +402,7 @@ __device__ __forceinline__ float rn_tf32(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int KC, bool TWO>
+template <int KC, bool TWO, bool GATHER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_dyn[];
@@ -433,6 +439,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   const int total_items = spc * p.nchunks;             // super-items
   const uint16_t cmask = (uint16_t)((1u << C) - 1u);
   const int G = p.seg_stages;
+  // this cluster's items: entries [k_begin, k_end) of the static schedule, or round-robin
+  const int k_begin = p.sched ? __ldg(p.sched + cid) : 0;
+  const int k_end = p.sched ? __ldg(p.sched + cid + 1)
+                            : (total_items - cid + n_clusters - 1) / n_clusters;
+#define SQ_FOR_ITEMS(...)                                                                \
+  for (int k_ = k_begin, nxt_ = (p.sched && k_begin < k_end) ? __ldg(p.sched + k_begin) : 0, \
+           item = p.sched ? nxt_ : cid;                                                  \
+       k_ < k_end;                                                                       \
+       ++k_, item = p.sched ? nxt_ : cid + k_ * n_clusters __VA_ARGS__)                  \
+    if (p.sched && k_ + 1 < k_end ? (nxt_ = __ldg(p.sched + k_ + 1), true) : true)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -469,7 +485,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       uint32_t st_ph = 0;
       long long w_empty = 0;
       const long long t_begin = clock64();
-      for (int item = cid; item < total_items; item += n_clusters) {
+      SQ_FOR_ITEMS() {
         const TcChunk ck = p.chunk[item / spc];
         int tile = (item % spc) * C + (int)crank;
         if (tile >= p.ntiles) tile = p.ntiles - 1;
@@ -489,7 +505,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           mbar_expect_tx(&full[s], ((p.ablate & 4) ? 0u : a_bytes) +
                                        ((p.ablate & 2) ? 0u : (uint32_t)(2 * B_BYTES)));
 #else
-          mbar_expect_tx(&full[s], (p.gather ? (uint32_t)(p.g_ph * p.g_box * 4) : a_bytes) +
+          mbar_expect_tx(&full[s], (GATHER ? (uint32_t)(p.g_ph * p.g_box * 4) : a_bytes) +
                                        (uint32_t)(2 * B_BYTES));
 #endif
           const int tl = i / p.kch, kc = i - tl * p.kch;
@@ -498,10 +514,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 #ifdef SQDET_ABLATE
           if (!(p.ablate & 4))
 #endif
-          if (p.gather) {
-            // patch rows at a 512-byte pitch; rows past the image bottom read the next image (or
-            // TMA zero fill past the tensor): they only feed conv pixels the epilogue masks
-            // TMA needs a 16-byte aligned global start: every row is fetched from its start
+          if (GATHER) {
+            // patch rows at a 512-byte pitch in the stage's A region.  TMA needs a 16-byte aligned global start: every row is fetched from its start
             // rounded down to 4 floats (the splitter adds the 0..3 float offset back); rows
             // above / below the image fetch a neighbour's data or zero fill, which the splitter
             // masks (padding) or which only feed conv pixels the epilogue masks
@@ -557,7 +571,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       int it = 0, g = 0, st_i = 0, n_item = 0;
       uint32_t st_ph = 0;
       long long w_split = 0, w_tempty = 0;
-      for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
+      SQ_FOR_ITEMS(, ++n_item) {
         const TcChunk ck = p.chunk[item / spc];
         const int iters = ck.tap_count * p.kch;
         const int owner = n_item & 1;                     // drain group of this item
@@ -624,7 +638,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     int it = 0, st_i = 0;
     uint32_t st_ph = 0;
     long long w_full = 0;
-    for (int item = cid; item < total_items; item += n_clusters) {
+    SQ_FOR_ITEMS() {
       const TcChunk ck = p.chunk[item / spc];
       const int iters = ck.tap_count * p.kch;
       for (int i = 0; i < iters; ++i, ++it) {
@@ -634,7 +648,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         SQ_TIMED_WAIT(w_full, &full[s], ph);
         // row t of the raw tile (KC*4 bytes, swizzled 16-byte chunks) -> registers ->
         // a_hi / a_lo -> TMEM slot s, lane t (this warp owns lanes 32*(warp%4)..+31)
-        if (KC == 32 && p.gather) {
+        if (KC == 32 && GATHER) {
           // gather mode: row t of A = the 27 taps (dy, dx, c) of conv pixel t, read from the
           // patch rows; taps outside the image (SAME padding), taps 27..31 and rows past the
           // tile are zero
@@ -737,7 +751,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     long long w_tfull = 0, c_epi = 0, c_stw = 0, c_pool = 0, c_par = 0;
     int n_item = 0, n_own = 0, n_store = 0;
     uint32_t use0 = 0u, use1 = 0u;               // own segments seen per TMEM buffer
-    for (int item = cid; item < total_items; item += n_clusters, ++n_item) {
+    SQ_FOR_ITEMS(, ++n_item) {
       const TcChunk ck = p.chunk[item / spc];
       const int iters = ck.tap_count * p.kch;
       if ((n_item % ngroups) != dgroup) {
@@ -1043,6 +1057,7 @@ struct TcImpl {
   long long npix = 0;
   float* d_scratch = nullptr;
   float* y_final = nullptr;
+  int* d_sched = nullptr;      // static LPT schedule (see TcParams::sched)
   // gather mode: the input address is baked into the 1-D tensor map; the engine feeds the first
   // layer from several buffers (pipelined inputs), so maps are cached per address
   long long x_floats = 0;
@@ -1193,6 +1208,50 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     P.sq_w = 32; P.sq_h = 0;
   }
   const bool pooled = pool && pool->size > 0;
+  // TMA-store epilogue: needs every chunk to be a whole number of 32-channel groups unless it
+  // ends at the tensor's last channel (where the TMA unit clips the tail).
+  bool store_ok = (y_cstride % 4 == 0);
+  {
+    static int env_tma = -1;
+    if (env_tma < 0) {
+      const char* a = getenv("SQDET_TC_TMA_STORE");
+      env_tma = a ? atoi(a) : 1;
+    }
+    if (!env_tma) store_ok = false;
+    for (auto& c : im->chunks)
+      if ((c.ch_count % 32) != 0 && (c.y_coff + c.ch_count != y_cstride)) store_ok = false;
+    for (auto& c : im->chunks)
+      if (c.y_coff % 4 != 0) store_ok = false;
+  }
+  if (!store_ok && !pooled && !flat && !gs) {
+    // Direct-store epilogue: any ct_h x ct_w <= 128 tile works, so pick the shape with the fewest
+    // rounds of the persistent grid (ConvDet head on 22x76x20: 8x16 tiles = 900 split-K items =
+    // 7 rounds on 148 SMs; 11x11 tiles = 840 items = 6 rounds), then the fewest tiles.
+    static int env_search = -1;
+    if (env_search < 0) {
+      const char* a = getenv("SQDET_TC_TILESEARCH");
+      env_search = a ? atoi(a) : 1;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long nch = (long long)im->chunks.size();
+    auto rounds_of = [&](long long tiles) { return (tiles * nch + sms - 1) / sms; };
+    long long best_tiles = (long long)B * P.tiles_h * P.tiles_w;
+    long long best_rounds = rounds_of(best_tiles);
+    for (int th = 1; env_search && th <= 32; ++th) {
+      int twd = TILE_M / th;
+      if (twd > 128) twd = 128;
+      if (twd < 4) break;
+      const long long tiles = (long long)B * ((H + th - 1) / th) * ((W + twd - 1) / twd);
+      const long long rounds = rounds_of(tiles);
+      if (rounds < best_rounds || (rounds == best_rounds && tiles < best_tiles * 9 / 10)) {
+        best_rounds = rounds; best_tiles = tiles;
+        P.ct_h = th; P.ct_w = twd; P.step_h = th; P.step_w = twd;
+        P.tiles_h = (H + th - 1) / th; P.tiles_w = (W + twd - 1) / twd;
+      }
+    }
+  }
   if (pooled) {
     // conv tile = the conv pixels under a pt_h x pt_w block of stride-2 pooling windows
     if (pool->size != 2 && pool->size != 3) return 0;
@@ -1301,6 +1360,50 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     long long nclusters = (long long)(sms * ctas) / cluster;
     if (supers < nclusters) nclusters = supers;
     im->grid = dim3((unsigned)(nclusters * cluster));
+    // Static longest-processing-time-first schedule when chunks differ in cost (a fire expand
+    // pair: 1x1 items of kch stages, 3x3 items of 9*kch): round-robin leaves e.g. 12 of 148 CTAs
+    // with 7 expensive items against 6 (207 vs 182 stages on fire10); LPT hands those CTAs
+    // fewer cheap items instead.
+    static int env_lpt = -1;
+    if (env_lpt < 0) {
+      const char* a = getenv("SQDET_TC_LPT");
+      env_lpt = a ? atoi(a) : 1;
+    }
+    bool differ = false;
+    for (auto& c : im->chunks)
+      if (c.tap_count != im->chunks[0].tap_count) differ = true;
+    // (only when a CTA gets few items: with dozens per CTA round-robin is already balanced, and
+    // keeping a tile's 1x1 and 3x3 items adjacent in time is better for L2 - measured on fire2/3)
+    if (env_lpt && differ && supers > nclusters && supers < 24 * nclusters) {
+      const int spc_h = (P.ntiles + cluster - 1) / cluster;
+      std::vector<int> order(im->chunks.size());
+      for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+      auto cost_of = [&](int c) { return 2 * im->chunks[c].tap_count * kch + 3; };   // + epilogue
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost_of(a) > cost_of(b); });
+      typedef std::pair<long long, int> Bin;     // (load, cluster id): least loaded first
+      std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> heap;
+      for (int b = 0; b < (int)nclusters; ++b) heap.push(Bin(0, b));
+      std::vector<std::vector<int>> lists((size_t)nclusters);
+      for (int c : order)
+        for (int t = 0; t < spc_h; ++t) {
+          Bin b = heap.top();
+          heap.pop();
+          lists[(size_t)b.second].push_back(c * spc_h + t);
+          b.first += cost_of(c);
+          heap.push(b);
+        }
+      std::vector<int> sched((size_t)nclusters + 1);
+      int pos = (int)nclusters + 1;
+      for (int b = 0; b < (int)nclusters; ++b) {
+        sched[(size_t)b] = pos;
+        pos += (int)lists[(size_t)b].size();
+      }
+      sched[(size_t)nclusters] = pos;
+      for (auto& l : lists) sched.insert(sched.end(), l.begin(), l.end());
+      SQ_CUDA(cudaMalloc(&im->d_sched, sizeof(int) * sched.size()));
+      SQ_CUDA(cudaMemcpy(im->d_sched, sched.data(), sizeof(int) * sched.size(), cudaMemcpyHostToDevice));
+      P.sched = im->d_sched;
+    }
   }
   P.y = y_dev;
   SQ_CUDA(cudaMalloc(&im->d_w, sizeof(float) * (size_t)row * 2 * KC));
@@ -1333,19 +1436,8 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     rc = encode_act_map(&P.tmA, x_dev, B, H, W, Cin, KC, P.ct_w, P.ct_h);
     if (rc) return rc;
   }
-  // TMA-store epilogue: needs every chunk to be a whole number of 32-channel groups unless it
-  // ends at the tensor's last channel (where the TMA unit clips the tail).
   {
-    static int env_tma = -1;
-    if (env_tma < 0) {
-      const char* a = getenv("SQDET_TC_TMA_STORE");
-      env_tma = a ? atoi(a) : 1;
-    }
-    bool ok = env_tma != 0 && (y_cstride % 4 == 0);
-    for (auto& c : im->chunks)
-      if ((c.ch_count % 32) != 0 && (c.y_coff + c.ch_count != y_cstride)) ok = false;
-    for (auto& c : im->chunks)
-      if (c.y_coff % 4 != 0) ok = false;
+    const bool ok = store_ok;
     if (pooled && !ok) return 0;          // the fused pool exists only on the TMA-store path
     if (ok) {
       if (pooled)
@@ -1367,13 +1459,15 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   // not per launch, so it must cover the largest plan)
   static bool attr_set = false;
   if (!attr_set) {
-    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false>,
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, false>,
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true>,
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, true>,
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, true, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
@@ -1447,10 +1541,12 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
   }
   if (prm.cluster <= 1) {
     // classic launch (no cluster attribute: keeps the non-cluster CTA->SM placement path)
-    if (im->KC == 32)
-      conv_tc_kernel<32, false><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+    if (prm.gather)
+      conv_tc_kernel<32, false, true><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+    else if (im->KC == 32)
+      conv_tc_kernel<32, false, false><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
     else
-      conv_tc_kernel<16, false><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+      conv_tc_kernel<16, false, false><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = im->grid;
@@ -1466,11 +1562,11 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     cfg.numAttrs = 1;
     cudaError_t le;
     if (prm.two_cta)
-      le = (im->KC == 32) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, true>, prm)
-                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true>, prm);
+      le = (im->KC == 32) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, true, false>, prm)
+                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true, false>, prm);
     else
-      le = (im->KC == 32) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, false>, prm)
-                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false>, prm);
+      le = (im->KC == 32) ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, false, false>, prm)
+                          : cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false, false>, prm);
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(conv_tc_kernel)");
   }
   SQ_CHECK_LAUNCH("conv_tc_kernel");
@@ -1492,10 +1588,10 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     for (int b = 0; b < nb; ++b)
       for (int k = 0; k < 12; ++k) a[k] += (double)h[(size_t)b * 12 + k] / nb;
     fprintf(stderr,
-            "[tc] grid %d cluster %d%s smem %zu KC %d N %d kch %d chunks %d stages %d seg %d | per-CTA avg cycles: "
+            "[tc] grid %d tile %dx%d ntiles %d%s cluster %d%s smem %zu KC %d N %d kch %d chunks %d stages %d seg %d | per-CTA avg cycles: "
             "total %.0f stages %.0f | waits: producer(empty) %.0f mma(split) %.0f mma(tempty) %.0f "
             "splitter(full) %.0f drain(tfull) %.0f | epilogue %.0f (store-wait %.0f, pool %.0f, params %.0f)\n",
-            nb, prm.cluster, prm.two_cta ? " (cta_group::2)" : "", im->smem_bytes, im->KC, prm.N, prm.kch, prm.nchunks, prm.stages, prm.seg_stages,
+            nb, prm.ct_h, prm.ct_w, prm.ntiles, prm.sched ? " LPT" : "", prm.cluster, prm.two_cta ? " (cta_group::2)" : "", im->smem_bytes, im->KC, prm.N, prm.kch, prm.nchunks, prm.stages, prm.seg_stages,
             a[5], a[6], a[0], a[1], a[2], a[3], a[4], a[7], a[8], a[9], a[10]);
   }
   return SQDET_OK;
@@ -1509,6 +1605,7 @@ static void release_impl(void** impl) {
   cudaFree(im->d_scale);
   cudaFree(im->d_shift);
   cudaFree(im->d_scratch);
+  cudaFree(im->d_sched);
   delete im;
   *impl = nullptr;
 }

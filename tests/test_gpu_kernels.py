@@ -23,6 +23,13 @@ CONV_CASES = [
     (1, 12, 20, 256, 72, 3, 1, 'SAME'),    # ConvDet head (N=72)
     (1, 17, 23, 64, 128, 1, 2, 'SAME'),    # ResNet strided 1x1
     (1, 20, 20, 32, 32, 3, 1, 'SAME'),
+    # first-layer gather mode (3x3 over 3 channels): every stride / padding / alignment class
+    (1, 33, 65, 3, 64, 3, 2, 'VALID'),     # odd row pitch: patch rows start 4-, 8-, 12-byte misaligned
+    (2, 34, 70, 3, 64, 3, 2, 'SAME'),      # even dims: zero padding only at the bottom / right
+    (2, 13, 29, 3, 64, 3, 1, 'SAME'),      # VGG conv1_1 shape class (pad 1 on all sides)
+    (1, 48, 100, 3, 96, 3, 1, 'VALID'),
+    (1, 64, 96, 64, 64, 1, 1, 'SAME'),     # flat 1x1 tiling, 48 whole tiles
+    (3, 11, 13, 32, 48, 1, 1, 'SAME'),     # flat 1x1 tiling, ragged last tile
 ]
 
 
