@@ -135,6 +135,29 @@ struct TcParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// Explicit shared-window accesses.  The dynamic smem base is re-aligned through integer
+// arithmetic, after which nvcc no longer knows the pointers are shared and emits generic
+// LD.E / ST.E (64-bit address math, longer latency) - every hot smem access goes through these.
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -183,11 +206,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap* map, int c0, int c1,
+__device__ __forceinline__ void tma_store_4d(uint32_t src, const CUtensorMap* map, int c0, int c1,
                                              int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -201,25 +224,24 @@ __device__ __forceinline__ void tma_store_wait_read_all() {
 // Conv staging: per 32-channel group a 128-row x 128 B tile (16 KB, 128B-swizzled), conv tile
 // width 14 + PK; pooled staging: per group a (pt_h*8)-row x 128 B tile (4 KB apart).
 template <int PK>
-__device__ __forceinline__ void pool_unit(const uint8_t* conv_base, uint8_t* pool_base, int u,
-                                          int n_pp) {
+__device__ __forceinline__ void pool_unit(uint32_t conv_base, uint32_t pool_base, int u, int n_pp) {
   constexpr int CTW = 14 + PK;
   const int k2 = u & 7;
   const int pu = u >> 3;
   const int jg = pu / n_pp, pp = pu - jg * n_pp;
   const int py = pp >> 3, px = pp & 7;
-  const uint8_t* tc = conv_base + jg * 16384;
+  const uint32_t tc = conv_base + (uint32_t)(jg * 16384);
   float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 #pragma unroll
   for (int a = 0; a < PK; ++a)
 #pragma unroll
     for (int b = 0; b < PK; ++b) {
       const int rr = (2 * py + a) * CTW + 2 * px + b;
-      const float4 q4 = *reinterpret_cast<const float4*>(tc + rr * 128 + ((k2 ^ (rr & 7)) << 4));
+      const float4 q4 = lds128(tc + (uint32_t)(rr * 128 + ((k2 ^ (rr & 7)) << 4)));
       m.x = fmaxf(m.x, q4.x); m.y = fmaxf(m.y, q4.y);
       m.z = fmaxf(m.z, q4.z); m.w = fmaxf(m.w, q4.w);
     }
-  *reinterpret_cast<float4*>(pool_base + jg * 4096 + pp * 128 + ((k2 ^ (pp & 7)) << 4)) = m;
+  sts128(pool_base + (uint32_t)(jg * 4096 + pp * 128 + ((k2 ^ (pp & 7)) << 4)), m);
 }
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -427,6 +449,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   // two 16 KB output staging tiles (128 pixels x 32 channels, 128B-swizzled) for TMA stores
   uint8_t* s_out = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(s_par + 4 * 3 * MAX_N) + 1023) & ~uintptr_t(1023));
+
+  // 32-bit shared-window addresses of the regions above (see lds128 / sts128)
+  const uint32_t smem_b = smem_u32(smem);
+  const uint32_t par_b = smem_b + (uint32_t)(reinterpret_cast<uint8_t*>(s_par) - smem);
+  const uint32_t out_b = smem_b + (uint32_t)(s_out - smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work decomposition: a cluster of C CTAs walks "super-items" = C consecutive tiles of one
@@ -652,7 +679,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           // gather mode: row t of A = the 27 taps (dy, dx, c) of conv pixel t, read from the
           // patch rows; taps outside the image (SAME padding), taps 27..31 and rows past the
           // tile are zero
-          const float* patch = reinterpret_cast<const float*>(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t patch = smem_b + (uint32_t)(s * STAGE_BYTES);
           int tile = (item % spc) * C + (int)crank;
           if (tile >= p.ntiles) tile = p.ntiles - 1;
           const int tw = tile % p.tiles_w;
@@ -666,14 +693,14 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           // global element index of (row iy0, tile's first patch column): its low 2 bits are the
           // offset the producer's 16-byte alignment shifted this patch row by
           const int g0 = ((img * p.g_H + iy0) * p.g_W + (w0 * p.g_stride - p.g_pad_l)) * 3;
-          const float* prow[3];
+          uint32_t prow[3];
           bool rok[3], cok[3];
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const int g = g0 + d * p.g_W * 3;
-            prow[d] = patch + (live ? (r_h * p.g_stride + d) * GATHER_PITCH + (g & 3) +
-                                          r_w * p.g_stride * 3
-                                    : 0);
+            prow[d] = patch + 4u * (uint32_t)(live ? (r_h * p.g_stride + d) * GATHER_PITCH + (g & 3) +
+                                                        r_w * p.g_stride * 3
+                                                  : 0);
             rok[d] = live && (iy0 + d) >= 0 && (iy0 + d) < p.g_H;
             cok[d] = (ix0 + d) >= 0 && (ix0 + d) < p.g_W;
           }
@@ -687,7 +714,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               const int k = hblk * 16 + e;
               float v = 0.f;
               if (k < 27) {
-                v = prow[k / 9][k % 9];
+                v = lds32(prow[k / 9] + 4u * (uint32_t)(k % 9));
                 if (!(rok[k / 9] && cok[(k % 9) / 3])) v = 0.f;
               }
               const float h = rn_tf32(v);
@@ -703,7 +730,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           else mbar_arrive(&split[s]);
           continue;
         }
-        const uint8_t* arow = smem + (size_t)s * STAGE_BYTES + (size_t)t * (KC * 4);
+        const uint32_t arow = smem_b + (uint32_t)(s * STAGE_BYTES + t * (KC * 4));
         const int sw = (KC == 32) ? (t & 7) : ((t >> 1) & 3);
         const uint32_t a_slot = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
                                 (uint32_t)(2 * p.N + s * 2 * KC);
@@ -716,7 +743,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int chunk = hblk * 4 + k;
-            const float4 v = *reinterpret_cast<const float4*>(arow + ((chunk ^ sw) << 4));
+            const float4 v = lds128(arow + (uint32_t)((chunk ^ sw) << 4));
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -769,13 +796,15 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const int ncols = (ck.ch_count + 15) & ~15;
       // stage this item's bias / scale / shift in smem (one element per drain thread); the
       // named barrier also orders it against the previous item's epilogue reads.
-      float* par = s_par + (dgroup * 2 + (n_own & 1)) * 3 * MAX_N;
+      const uint32_t par = par_b + 4u * (uint32_t)((dgroup * 2 + (n_own & 1)) * 3 * MAX_N);
       const long long tpar0 = p.dbg ? clock64() : 0;
       {
         const bool in = tt < ck.ch_count;
-        par[tt] = (in && p.bias) ? __ldg(p.bias + ck.bias_base + tt) : 0.f;
-        par[MAX_N + tt] = (in && p.scale) ? __ldg(p.scale + ck.bias_base + tt) : 1.f;
-        par[2 * MAX_N + tt] = (in && p.scale) ? __ldg(p.shift + ck.bias_base + tt) : 0.f;
+        sts32(par + 4u * (uint32_t)tt, (in && p.bias) ? __ldg(p.bias + ck.bias_base + tt) : 0.f);
+        sts32(par + 4u * (uint32_t)(MAX_N + tt),
+              (in && p.scale) ? __ldg(p.scale + ck.bias_base + tt) : 1.f);
+        sts32(par + 4u * (uint32_t)(2 * MAX_N + tt),
+              (in && p.scale) ? __ldg(p.shift + ck.bias_base + tt) : 0.f);
         asm volatile("bar.sync %0, 128;" ::"r"(1 + dgroup) : "memory");
       }
       if (p.dbg) c_par += clock64() - tpar0;
@@ -831,24 +860,24 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 if (p.dbg) c_stw += clock64() - t0;
               }
               __syncwarp();
-              uint8_t* tile_w = s_out + (dgroup * 4 + q) * (4096 * p.store_ring) +
-                                (p.store_ring == 2 ? (n_store & 1) * 4096 : 0);
+              const uint32_t tile_w = out_b + (uint32_t)((dgroup * 4 + q) * (4096 * p.store_ring) +
+                                                         (p.store_ring == 2 ? (n_store & 1) * 4096 : 0));
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int c = jg * 32 + k * 4;
-                const float4 b0 = *reinterpret_cast<const float4*>(par + c);
+                const float4 b0 = lds128(par + 4u * (uint32_t)c);
                 float o[4] = {acc[c] + b0.x, acc[c + 1] + b0.y, acc[c + 2] + b0.z,
                               acc[c + 3] + b0.w};
                 if (affine) {
-                  const float4 s0 = *reinterpret_cast<const float4*>(par + MAX_N + c);
-                  const float4 h0v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c);
+                  const float4 s0 = lds128(par + 4u * (uint32_t)(MAX_N + c));
+                  const float4 h0v = lds128(par + 4u * (uint32_t)(2 * MAX_N + c));
                   o[0] = o[0] * s0.x + h0v.x; o[1] = o[1] * s0.y + h0v.y;
                   o[2] = o[2] * s0.z + h0v.z; o[3] = o[3] * s0.w + h0v.w;
                 }
                 float4 v;
                 v.x = fmaxf(o[0], lo_clip); v.y = fmaxf(o[1], lo_clip);
                 v.z = fmaxf(o[2], lo_clip); v.w = fmaxf(o[3], lo_clip);
-                *reinterpret_cast<float4*>(tile_w + lane * 128 + ((k ^ (lane & 7)) << 4)) = v;
+                sts128(tile_w + (uint32_t)(lane * 128 + ((k ^ (lane & 7)) << 4)), v);
               }
               fence_async_proxy();
               __syncwarp();
@@ -871,16 +900,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
           for (int jg = 0; jg < MAX_N / 32; ++jg) {
             if (jg * 32 < ck.ch_count) {
-              uint8_t* tile_c = s_out + dgroup * POOL_STAGE_BYTES + jg * 16384;
+              const uint32_t tile_c = out_b + (uint32_t)(dgroup * POOL_STAGE_BYTES + jg * 16384);
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int c = jg * 32 + k * 4;
-                const float4 b0 = *reinterpret_cast<const float4*>(par + c);
+                const float4 b0 = lds128(par + 4u * (uint32_t)c);
                 float o[4] = {acc[c] + b0.x, acc[c + 1] + b0.y, acc[c + 2] + b0.z,
                               acc[c + 3] + b0.w};
                 if (affine) {
-                  const float4 s0 = *reinterpret_cast<const float4*>(par + MAX_N + c);
-                  const float4 h0v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c);
+                  const float4 s0 = lds128(par + 4u * (uint32_t)(MAX_N + c));
+                  const float4 h0v = lds128(par + 4u * (uint32_t)(2 * MAX_N + c));
                   o[0] = o[0] * s0.x + h0v.x; o[1] = o[1] * s0.y + h0v.y;
                   o[2] = o[2] * s0.z + h0v.z; o[3] = o[3] * s0.w + h0v.w;
                 }
@@ -890,7 +919,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 v.y = pix_ok ? fmaxf(o[1], lo_clip) : ninf;
                 v.z = pix_ok ? fmaxf(o[2], lo_clip) : ninf;
                 v.w = pix_ok ? fmaxf(o[3], lo_clip) : ninf;
-                *reinterpret_cast<float4*>(tile_c + r * 128 + ((k ^ (r & 7)) << 4)) = v;
+                sts128(tile_c + (uint32_t)(r * 128 + ((k ^ (r & 7)) << 4)), v);
               }
             }
           }
@@ -899,8 +928,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           // unit = (channel group jg, pooled pixel pp, 16-byte chunk k2); pt_w == 8
           const int n_pp = p.pt_h * 8;
           const int n_units = ((ck.ch_count + 31) >> 5) * n_pp * 8;
-          const uint8_t* conv_base = s_out + dgroup * POOL_STAGE_BYTES;
-          uint8_t* pool_base = s_out + dgroup * POOL_STAGE_BYTES + POOL_MAX_GROUPS * 16384;
+          const uint32_t conv_base = out_b + (uint32_t)(dgroup * POOL_STAGE_BYTES);
+          const uint32_t pool_base = conv_base + (uint32_t)(POOL_MAX_GROUPS * 16384);
           if (p.pool == 3) {
             for (int u = tt; u < n_units; u += 128)
               pool_unit<3>(conv_base, pool_base, u, n_pp);
@@ -929,16 +958,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         for (int c = 0; c < MAX_N; c += 8) {
           if (c < ck.ch_count) {
             float o[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(par + c);
-            const float4 b1 = *reinterpret_cast<const float4*>(par + c + 4);
+            const float4 b0 = lds128(par + 4u * (uint32_t)c);
+            const float4 b1 = lds128(par + 4u * (uint32_t)(c + 4));
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = acc[c + e] + bb[e];
             if (affine) {
-              const float4 s0 = *reinterpret_cast<const float4*>(par + MAX_N + c);
-              const float4 s1 = *reinterpret_cast<const float4*>(par + MAX_N + c + 4);
-              const float4 h0v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c);
-              const float4 h1v = *reinterpret_cast<const float4*>(par + 2 * MAX_N + c + 4);
+              const float4 s0 = lds128(par + 4u * (uint32_t)(MAX_N + c));
+              const float4 s1 = lds128(par + 4u * (uint32_t)(MAX_N + c + 4));
+              const float4 h0v = lds128(par + 4u * (uint32_t)(2 * MAX_N + c));
+              const float4 h1v = lds128(par + 4u * (uint32_t)(2 * MAX_N + c + 4));
               const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
               const float hh[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
 #pragma unroll
