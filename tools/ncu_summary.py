@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Turn ncu output into the small tracked summaries under profiles/.
+
+  launches <launch_list.csv> <out_prefix>   metrics-only pass of `bench.py --steps 2 --warmup 1`
+                                            -> <out_prefix>_launch_shares.csv (one forward)
+  full <raw_page.csv> <out_prefix>          `ncu -i X.ncu-rep --page raw --csv` of one forward
+                                            -> <out_prefix>_ncu_full.csv and <out_prefix>_traffic.json
+
+Launches are mapped to engine ops by their order inside one SqueezeDet forward."""
+import csv, json, sys
+
+OPS = (['conv1+pool1'] + ['fire2.squeeze', 'fire2.expand', 'fire3.squeeze', 'fire3.expand', 'pool3',
+       'fire4.squeeze', 'fire4.expand', 'fire5.squeeze', 'fire5.expand', 'pool5'] +
+       [f'fire{i}.{p}' for i in range(6, 12) for p in ('squeeze', 'expand')] +
+       ['conv12.partials', 'conv12.reduce', 'interpret_output', 'filter_prediction'])
+N = len(OPS)   # 27 kernel launches per forward
+
+def read_rows(path):
+  rows = list(csv.reader(l for l in open(path) if not l.startswith('==')))
+  hdr = next(r for r in rows if 'Kernel Name' in r)
+  body = [r for r in rows[rows.index(hdr) + 1:] if len(r) == len(hdr)]
+  return hdr, body
+
+def forward_start(names):
+  """index of the last complete forward: starts at a conv_pool_simt launch, ends at filter."""
+  starts = [i for i, n in enumerate(names) if 'conv_pool_simt' in n and i + N <= len(names)
+            and 'filter_kernel' in names[i + N - 1]]
+  if not starts:
+    raise SystemExit('no complete forward (%d launches) found' % N)
+  return starts[-1]
+
+def launches(path, prefix):
+  hdr, body = read_rows(path)
+  i_id, i_k, i_m, i_v = hdr.index('ID'), hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Value')
+  dur = [(r[i_k], float(r[i_v].replace(',', ''))) for r in body if r[i_m] == 'gpu__time_duration.sum']
+  names = [n for n, _ in dur]
+  s = forward_start(names)
+  fw = dur[s:s + N]
+  tot = sum(v for _, v in fw)
+  with open(prefix + '_launch_shares.csv', 'w') as f:
+    f.write('# one forward (27 launches) out of the ncu launch list of `bench.py --steps 2 --warmup 1`\n')
+    f.write('# cold-cache, serialised under the profiler: compare SHARES, not absolutes\n')
+    f.write('op,kernel,duration_us,share\n')
+    for op, (n, v) in zip(OPS, fw):
+      short = n.split('(')[0].split('::')[-1].replace('void ', '')
+      f.write('%s,%s,%.2f,%.4f\n' % (op, short, v / 1e3, v / tot))
+    f.write('total,,%.2f,1.0\n' % (tot / 1e3))
+  print('forward at launch', s, 'total %.1f us' % (tot / 1e3))
+
+KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__grid_size', 'launch__block_size', 'sm__cycles_elapsed.max']
+
+def full(path, prefix):
+  rows = list(csv.reader(open(path)))
+  hdr = rows[0]
+  units = rows[1]
+  body = rows[2:]
+  i_k = hdr.index('Kernel Name')
+  names = [r[i_k] for r in body]
+  s = forward_start(names) if len(names) > N else 0
+  cols = [(m, hdr.index(m)) for m in KEEP if m in hdr]
+  def num(x):
+    try: return float(x.replace(',', ''))
+    except ValueError: return float('nan')
+  scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+  traffic = {}
+  with open(prefix + '_ncu_full.csv', 'w') as f:
+    f.write('# ncu --set full --clock-control none --import-source on, one SqueezeDet forward (1242x375, b=20, one B200)\n')
+    f.write('# units: ' + ', '.join('%s[%s]' % (m, units[i]) for m, i in cols) + '\n')
+    f.write('op,' + ','.join(m for m, _ in cols) + '\n')
+    for op, r in zip(OPS, body[s:s + N]):
+      f.write(op + ',' + ','.join(r[i] for _, i in cols) + '\n')
+      rd = num(r[hdr.index('dram__bytes_read.sum')]) * scale.get(units[hdr.index('dram__bytes_read.sum')], 1.0)
+      wr = num(r[hdr.index('dram__bytes_write.sum')]) * scale.get(units[hdr.index('dram__bytes_write.sum')], 1.0)
+      key = op.split('.')[0].replace('conv1+pool1', 'conv1')
+      traffic[key] = traffic.get(key, 0.0) + rd + wr
+  json.dump({'source': 'ncu --set full capture of this round (%s_ncu_full.csv): dram__bytes_read.sum + '
+                       'dram__bytes_write.sum per launch, summed over the launches of an op' % prefix,
+             'bytes_per_op': traffic}, open(prefix + '_traffic.json', 'w'), indent=1)
+  print('wrote', prefix + '_ncu_full.csv', prefix + '_traffic.json')
+
+if __name__ == '__main__':
+  {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
