@@ -238,6 +238,9 @@ def run_ours(args):
     raise SystemExit('bench.py: no CUDA device visible; the engine has no CPU fallback')
   torch.cuda.set_device(local)
   if world > 1:
+    # stdout carries exactly one JSON line: keep NCCL's version banner off it
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+      os.environ['NCCL_DEBUG'] = 'WARN'
     dist.init_process_group('nccl', rank=rank, world_size=world,
                             device_id=torch.device('cuda', local))
 
@@ -386,6 +389,10 @@ def run_ours(args):
                 'frac': ach / peak, 'traffic': traffic,
                 'traffic_source': 'profiles/r1_traffic.json (ncu dram bytes, same workload)' if traffic else None, 'peak_source': peaks['source'],
                 'kernel_ms': float(acc[top]), 'kernel_share_of_step': float(acc[top] / acc.sum()),
+                # context for FFMA kernels (the fused first layer): algorithmic TFLOP/s next to the
+                # fp32 SIMT peak of this part (SMs x 128 lanes x 2 flop x SM clock)
+                'achieved_tflops': fl / sec / 1e12,
+                'fp32_simt_peak_tflops': 148 * 128 * 2 * (clocks['sm_mhz'] if clocks and clocks.get('sm_mhz') else 1965.0) * 1e6 / 1e12,
                 'algorithmic_bytes_per_launch': by, 'algorithmic_flops_per_launch': fl,
                 'whole_step': {'algorithmic_gbytes': tot_by / 1e9, 'gflop': tot_fl / 1e9,
                                'hbm_gbs': tot_by / (ms_per_step * 1e-3) / 1e9,
