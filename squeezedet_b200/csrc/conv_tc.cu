@@ -2,44 +2,49 @@
 //
 // Replaces tf.nn.conv2d + bias_add [+ batch_normalization] + relu of the reference
 // (src/nn_skeleton.py:539-547, :441-449) for every stride-1 conv whose Cin is a multiple
-// of 16 (all fire squeeze/expand convs, the ConvDet head, the VGG/ResNet body), and fuses
-// a fire module's expand1x1 || expand3x3 + channel concat (src/nets/squeezeDet.py:96-106)
-// into one launch.
+// of 16 (all fire squeeze/expand convs, the ConvDet head, the VGG/ResNet body) and for 3x3
+// convs over 3-channel images ("gather mode"), and fuses a fire module's expand1x1 ||
+// expand3x3 + channel concat (src/nets/squeezeDet.py:96-106) into one launch.
 //
 // GEMM view per CTA:  D[128 pixels, N] += A[128 pixels, K] * W[K, N]
-//   M tile  = an 8 x 16 patch of output pixels of one image (TMEM lane = pixel)
-//   N       = one chunk of output channels (multiple of 16, <= 256; TMEM column = channel)
+//   M tile  = an 8 x 16 patch of output pixels of one image (TMEM lane = pixel); 128 consecutive
+//             pixels of the flattened B*H*W list when the launch holds only 1x1 convs; the conv
+//             pixels under a block of pooling windows when a stride-2 max-pool is fused
+//   N       = one chunk of output channels (multiple of 16, <= 128; TMEM column = channel)
 //   K       = taps x Cin, walked as (tap, 32- or 16-channel chunk)
 //   A       : TMA tiled load of the NHWC activation tensor, box {KC ch, 16 w, 8 h, 1 n} at
 //             the tap-shifted coordinate; out-of-image coordinates are zero-filled by the
 //             TMA unit = TF "SAME" zero padding; lands K-major with the 128B/64B swizzle.
 //   W       : host-packed [chunk][tap][kchunk][N][KC] fp32 (hi and lo halves), 2-D TMA.
-// Precision: fp32 operands are split a = a_hi + a_lo with a_hi = rn_tf32(a),
-//   a_lo = rn_tf32(a - a_hi); D += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation
-//   in TMEM (kind::tf32).  Dropped term a_lo*b_lo ~ 2^-22: fp32-grade results, which the
+// Precision: fp32 operands are split a = a_hi + a_lo with a_hi = rn_tf32(a), a_lo = a - a_hi
+//   (exact; the tensor core reads its top 19 bits); D += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with
+//   fp32 accumulation in TMEM (kind::tf32).  Dropped terms ~ 2^-21: fp32-grade results, which the
 //   1e-4 parity bar against the fp32 reference needs through ~25 stacked convs (plain TF32
 //   or BF16 miss it by 1-2 orders of magnitude).  Weights are pre-split on the host.  The
 //   activation split is done by 4 warps between the TMA landing and the MMA issue: each thread
 //   reads its pixel's row of the raw tile from smem and writes a_hi / a_lo into TENSOR MEMORY
 //   (tcgen05.st); the MMAs take A from TMEM (.ts form) and only B from smem.  (With A in smem
-//   the kernel was shared-memory-bandwidth bound: 3 MMAs x (128+N) x 32 B per K step plus the
-//   splitter's own traffic ~ 2x the 128 B/clk/SM the SM has; measured, see DESIGN.md.)
+//   the kernel was shared-memory-bandwidth bound; measured, see DESIGN.md.)
 // Accumulation: the tensor core adds into its fp32 accumulator with truncation (measured
-//   on B200: error grows linearly with the number of chained MMAs, 3.6e-5 of max at K=6912
-//   vs 2e-6 for fp32 FFMA).  So a tile's K loop is cut into SEGMENTS of ~24 MMAs, each
+//   on B200: a systematic shrink, linear in the number of chained MMAs, 3.6e-5 of max at
+//   K=6912 vs 2e-6 for fp32 FFMA).  So a tile's K loop is cut into SEGMENTS of 36 MMAs, each
 //   accumulated from zero in one of two TMEM buffers; the drain warps add finished segments
-//   into fp32 registers (round-to-nearest).  Bias falls by sqrt(segment/total) (~15x at the
-//   ConvDet head) and the drain of segment g overlaps the MMAs of segment g+1.
-// Persistent CTAs (one per SM, 384 threads = 3 warpgroups), static round-robin over
-//   (chunk, tile) items:  warpgroup 0: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
-//   (one elected lane), warps 2-3 idle;  warpgroup 1 = operand splitter;  warpgroup 2 =
-//   segment drain + epilogue (tcgen05.ld -> fp32 add -> +bias [*scale+shift] -> relu -> TMA
-//   store); TWO drain warpgroups alternate items (measured: one drain group was the bottleneck
-//   of the small-K layers - the MMA warp spent 30-45 % of its time waiting for TMEM buffers).
-//   setmaxnreg moves registers from warpgroups 0/1 to the drain warpgroups, whose running sums
-//   (up to 128 per thread) must stay out of local memory.
+//   into fp32 registers (round-to-nearest) scaled by 1 + 1.4e-8 * (MMAs in the segment), the
+//   measured first-order size of the remaining bias; the drain of segment g overlaps the MMAs of
+//   segment g+1.
+// Persistent CTAs (one per SM, 512 threads = 4 warpgroups) over (chunk, tile) items, round-robin
+//   or a host-computed longest-processing-time-first schedule:  warpgroup 0: warp 0 = TMA
+//   producer, warp 1 = TMEM owner + MMA issuer (one elected lane), warps 2-3 idle;  warpgroup 1 =
+//   operand splitter;  warpgroups 2 and 3 = segment drain + epilogue (tcgen05.ld -> fp32 FFMA ->
+//   +bias [*scale+shift] -> relu -> TMA store), alternating items (measured: one drain group was
+//   the bottleneck of the small-K layers - the MMA warp spent 30-45 % of its time waiting for
+//   TMEM buffers).  setmaxnreg moves registers from warpgroups 0/1 to the drain warpgroups, whose
+//   running sums (up to 128 per thread) must stay out of local memory.
 // Pipelines: full[s] (TMA -> splitter), split[s] (splitter -> MMA), empty[s]
-//   (tcgen05.commit -> TMA), tfull[b] (tcgen05.commit -> drain), tempty[b] (drain -> MMA).
+//   (tcgen05.commit -> TMA), tfull[group][b] (tcgen05.commit -> drain), tempty[b] (drain -> MMA).
+// Opt-in variants kept for measurement (all parity-green, all slower today):
+//   weight-tile TMA multicast over CTA clusters, CTA-pair MMA (cta_group::2), fused max-pool
+//   epilogue; -DSQDET_ABLATE builds can switch pipeline pieces off (tools/ablate.sh).
 // Roofline: SqueezeDet fire2-9 are HBM-bound even fused (AI 24-95 FLOP/B fp32 I/O),
 //   fire10/11 ~ridge, ConvDet tensor-bound; 3xTF32 costs 3 MMAs at the
 //   TF32 rate per algorithmic MAC.

@@ -2,11 +2,13 @@
 """SqueezeDet demo — drop-in for reference ``src/demo.py`` (image mode and video mode), same
 flags: --mode --checkpoint --input_path --out_dir --demo_net --gpu.
 
-    python -m squeezedet_b200.demo --input_path './data/*.png' --checkpoint weights.npz
+    python -m squeezedet_b200.demo --input_path './data/*.png' \\
+        --checkpoint ./data/model_checkpoints/squeezeDet/model.ckpt-87000
 
-`--checkpoint` takes an .npz keyed by the reference's variable names (see utils/checkpoint.py;
-a TF-checkpoint reader is round-2 work) or the word `synthetic` for seeded random weights
-(plumbing run, SURVEY config 1).  Per image: cv2.imread -> float32 -> cv2.resize to
+`--checkpoint` takes the reference's own Saver path (TensorFlow V2 `.index/.data` bundle or V1
+table, read without TensorFlow: utils/tf_checkpoint.py), an .npz keyed by the reference's
+variable names, or the word `synthetic` for seeded random weights (plumbing run, SURVEY
+config 1).  Per image: cv2.imread -> float32 -> cv2.resize to
 (mc.IMAGE_WIDTH, mc.IMAGE_HEIGHT) -> minus mc.BGR_MEANS (reference demo.py:187-190) -> ONE GPU
 pass doing detect + filter_prediction (demo.py:193-199) -> keep prob > PLOT_PROB_THRESH -> draw ->
 imwrite out_<name>.
@@ -25,7 +27,7 @@ def parse_flags(argv=None):
   ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawTextHelpFormatter)
   ap.add_argument('--mode', default='image', help="'image' or 'video'.")
   ap.add_argument('--checkpoint', default='./data/model_checkpoints/squeezeDet/model.ckpt-87000',
-                  help='Path to the model parameter file (.npz) or "synthetic".')
+                  help='Path to the model parameter file: TF checkpoint, .npz, or "synthetic".')
   ap.add_argument('--input_path', default='./data/sample.png',
                   help='Input image or video to be detected. Can process glob input such as '
                        './data/00000*.png.')
@@ -48,7 +50,7 @@ def build_model(demo_net, gpu, checkpoint):
   if checkpoint == 'synthetic':
     model.load_weights(synth.synthetic_weights(synth.model_param_specs(model), seed=0))
   else:
-    model.load_weights(ckpt.load_npz(checkpoint))
+    model.load_weights(ckpt.load_weights_file(checkpoint))
   return mc, model
 
 

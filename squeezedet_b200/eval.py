@@ -29,7 +29,7 @@ def parse_flags(argv=None):
   ap.add_argument('--image_set', default='test', help='train, trainval, val, or test')
   ap.add_argument('--eval_dir', default='/tmp/bichen/logs/squeezeDet/eval')
   ap.add_argument('--checkpoint_path', default='/tmp/bichen/logs/squeezeDet/train',
-                  help='Parameter file (.npz keyed by reference variable names) or "synthetic".')
+                  help='TF checkpoint path, .npz keyed by reference variable names, or "synthetic".')
   ap.add_argument('--run_once', action='store_true', default=True)
   ap.add_argument('--net', default='squeezeDet', help='Neural net architecture.')
   ap.add_argument('--gpu', default='0', help='gpu id.')
@@ -79,7 +79,7 @@ def eval_once(flags):
   if flags.checkpoint_path == 'synthetic':
     model.load_weights(synth.synthetic_weights(synth.model_param_specs(model), seed=0))
   else:
-    model.load_weights(ckpt.load_npz(flags.checkpoint_path))
+    model.load_weights(ckpt.load_weights_file(flags.checkpoint_path))
 
   with open(os.path.join(flags.data_path, 'ImageSets', flags.image_set + '.txt')) as f:
     image_ids = [x.strip() for x in f.readlines()]

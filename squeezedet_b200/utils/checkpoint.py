@@ -1,9 +1,15 @@
-"""Weight files for the engine.  No TensorFlow checkpoint reader exists yet (SURVEY §8 f-2,
-round 2): weights are exchanged as ``.npz`` archives keyed by the reference's TF variable names
-(`conv1/kernels` HWIO, `fire2/squeeze1x1/biases`, BN `.../gamma|beta|mean|var`) — exactly the
-names `tf.train.Saver(model.model_params)` stores (reference src/demo.py:181) — or as the
-reference's Caffe-derived joblib ``.pkl`` ({layer: [W(out,in,h,w), b]}, src/nn_skeleton.py:492-508)."""
+"""Weight files for the engine, all keyed by the reference's TF variable names (`conv1/kernels`
+HWIO, `fire2/squeeze1x1/biases`, BN `.../gamma|beta|mean|var`) — exactly the names
+`tf.train.Saver(model.model_params)` stores (reference src/demo.py:181):
+
+* TensorFlow checkpoints, V2 bundles and V1 tables, read without TensorFlow
+  (`tf_checkpoint.py`; also written, so the reference's Saver can restore our weights);
+* ``.npz`` archives;
+* the reference's Caffe-derived joblib ``.pkl`` ({layer: [W(out,in,h,w), b]},
+  src/nn_skeleton.py:492-508)."""
 from __future__ import annotations
+
+import os
 
 import numpy as np
 
@@ -15,6 +21,26 @@ def load_npz(path):
 
 def save_npz(path, weights):
   np.savez(path, **{k: np.asarray(v, dtype=np.float32) for k, v in weights.items()})
+
+
+def load_weights_file(path):
+  """{variable name: ndarray} from whatever `--checkpoint` points at: an .npz, or the Saver path
+  of a TensorFlow checkpoint (``.../model.ckpt-87000``, as in reference src/demo.py:181-184)."""
+  from . import tf_checkpoint
+  if path.endswith('.npz'):
+    return load_npz(path)
+  if tf_checkpoint.checkpoint_kind(path):
+    return tf_checkpoint.read_checkpoint(path)
+  if os.path.exists(path + '.npz'):
+    return load_npz(path + '.npz')
+  raise FileNotFoundError('%s: no .npz archive and no TensorFlow checkpoint (V2 .index/.data or '
+                          'V1) at this path' % path)
+
+
+def save_tf_checkpoint(prefix, weights):
+  """Write a V2 checkpoint the reference's `saver.restore(sess, prefix)` accepts."""
+  from . import tf_checkpoint
+  tf_checkpoint.write_v2(prefix, {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()})
 
 
 def from_caffe_pkl(path, model):
