@@ -182,6 +182,16 @@ int sqdet_conv2d(const float* x_dev, const float* w_hwio_dev, const float* bias_
 /* tf.nn.max_pool NHWC (src/nn_skeleton.py:580-583).                                   */
 int sqdet_maxpool_nhwc(const float* x_dev, float* y_dev, int B, int H, int W, int C,
                        int size, int stride, int padding, void* stream);
+/* Image pre-processing in front of the path: uint8 BGR [src_h, src_w, 3] ->
+ * fp32 [dst_h, dst_w, 3], cv2.resize's float32 INTER_LINEAR plus the mean subtraction.
+ * order SQDET_PRE_RESIZE_THEN_SUB: src/demo.py:187-190 (astype(float32), resize, - BGR_MEANS);
+ * order SQDET_PRE_SUB_THEN_RESIZE: src/dataset/imdb.py:87-91 (astype(float32), -= BGR_MEANS,
+ * resize).  bgr_means: 3 doubles on the host.  dst may point into an engine input batch.  */
+#define SQDET_PRE_RESIZE_THEN_SUB 0
+#define SQDET_PRE_SUB_THEN_RESIZE 1
+int sqdet_preprocess_u8(const uint8_t* src_dev, int src_h, int src_w, float* dst_dev,
+                        int dst_h, int dst_w, const double* bgr_means, int order,
+                        void* stream);
 /* interpret_output (src/nn_skeleton.py:146-238,271-283; util.py:167-196,219-231).     */
 int sqdet_interpret(const float* preds_dev, const float* anchors_f32_dev,
                     float* det_boxes_dev, float* det_probs_dev, int64_t* det_class_dev,

@@ -1107,6 +1107,17 @@ int sqdet_maxpool_nhwc(const float* x_dev, float* y_dev, int B, int H, int W, in
   return launch_maxpool(x_dev, y_dev, B, H, W, C, size, stride, padding, (cudaStream_t)stream);
 }
 
+int sqdet_preprocess_u8(const uint8_t* src_dev, int src_h, int src_w, float* dst_dev, int dst_h,
+                        int dst_w, const double* bgr_means, int order, void* stream) {
+  if (!src_dev || !dst_dev || !bgr_means)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_preprocess_u8: null pointer");
+  if (order != SQDET_PRE_RESIZE_THEN_SUB && order != SQDET_PRE_SUB_THEN_RESIZE)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_preprocess_u8: order must be 0 (demo) or 1 (eval)");
+  return launch_resize_meansub_u8(src_dev, src_h, src_w, dst_dev, dst_h, dst_w, bgr_means[0],
+                                  bgr_means[1], bgr_means[2], order == SQDET_PRE_SUB_THEN_RESIZE,
+                                  (cudaStream_t)stream);
+}
+
 int sqdet_interpret(const float* preds_dev, const float* anchors_f32_dev, float* det_boxes_dev,
                     float* det_probs_dev, int64_t* det_class_dev, int B, int grid_h, int grid_w,
                     int anchors_per_grid, int classes, int image_width, int image_height,

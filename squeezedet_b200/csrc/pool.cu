@@ -122,7 +122,81 @@ u8_meansub_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long
   }
 }
 
+// uint8 BGR [H0, W0, 3] -> fp32 [H, W, 3]: cv2.resize (float32, INTER_LINEAR) and the mean
+// subtraction, in the reference's two orders (src/demo.py:187-190: resize, then `- BGR_MEANS`
+// in float64; src/dataset/imdb.py:87-91: float32 `-= BGR_MEANS`, then resize).  Restates
+// oracle/preproc.py operation for operation (double sampling position, float32 weight, clamps,
+// horizontal pass then vertical pass, round-to-nearest multiplies and adds, no contraction).
+// One thread = one output pixel (3 channels); the 4 taps are 12 byte loads served by L1.
+__global__ void __launch_bounds__(256)
+resize_meansub_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int H0, int W0,
+                         int H, int W, double scale_x, double scale_y, double m0, double m1,
+                         double m2, int sub_first) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)H * W) return;
+  const int dx = (int)(idx % W), dy = (int)(idx / W);
+  const double mean[3] = {m0, m1, m2};
+  int sx, sx1, y0, y1;
+  float fx, fy;
+  bool x_edge = false;
+  if (W == W0 && H == H0) {                    // cv2.resize returns a copy for equal sizes
+    sx = sx1 = dx; y0 = y1 = dy; fx = 0.f; fy = 0.f; x_edge = true;
+  } else {
+    // explicit round-to-nearest ops: an FMA contraction here could move a sampling position
+    // across an integer relative to the restatement
+    const double px = __dsub_rn(__dmul_rn(__dadd_rn((double)dx, 0.5), scale_x), 0.5);
+    const double py = __dsub_rn(__dmul_rn(__dadd_rn((double)dy, 0.5), scale_y), 0.5);
+    const double flx = floor(px), fly = floor(py);
+    sx = (int)flx;
+    fx = (float)(px - flx);
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= W0 - 1) { sx = W0 - 1; fx = 0.f; x_edge = true; }
+    sx1 = min(sx + 1, W0 - 1);
+    const int sy = (int)fly;
+    fy = (float)(py - fly);
+    y0 = min(max(sy, 0), H0 - 1);
+    y1 = min(max(sy + 1, 0), H0 - 1);
+  }
+  const float a0 = __fsub_rn(1.f, fx), a1 = fx, b0 = __fsub_rn(1.f, fy), b1 = fy;
+  const bool same = (W == W0 && H == H0);
+  float o[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float t[2][2];
+    const int ys[2] = {y0, y1}, xs[2] = {sx, sx1};
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float v = (float)src[((long long)ys[r] * W0 + xs[q]) * 3 + c];
+        t[r][q] = sub_first ? (float)((double)v - mean[c]) : v;
+      }
+    float row[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      row[r] = x_edge ? t[r][0] : __fadd_rn(__fmul_rn(t[r][0], a0), __fmul_rn(t[r][1], a1));
+    const float v = same ? row[0] : __fadd_rn(__fmul_rn(row[0], b0), __fmul_rn(row[1], b1));
+    o[c] = sub_first ? v : (float)((double)v - mean[c]);
+  }
+  float* d = dst + idx * 3;
+  d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+}
+
 }  // namespace
+
+int launch_resize_meansub_u8(const uint8_t* src, int H0, int W0, float* dst, int H, int W,
+                             double m0, double m1, double m2, int sub_first, cudaStream_t stream) {
+  if (H0 <= 0 || W0 <= 0 || H <= 0 || W <= 0)
+    return fail(SQDET_ERR_INVALID_ARG, "resize_meansub_u8: non-positive image size");
+  // cv::resize: inv_scale = dst / src, scale = 1 / inv_scale (both double)
+  const double scale_x = 1.0 / ((double)W / (double)W0);
+  const double scale_y = 1.0 / ((double)H / (double)H0);
+  const long long n = (long long)H * W;
+  resize_meansub_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+      src, dst, H0, W0, H, W, scale_x, scale_y, m0, m1, m2, sub_first);
+  SQ_CHECK_LAUNCH("resize_meansub_u8_kernel");
+  return SQDET_OK;
+}
 
 int launch_u8_meansub(const uint8_t* src, float* dst, int64_t n_pixels, double m0, double m1,
                       double m2, cudaStream_t stream) {

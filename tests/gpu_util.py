@@ -81,3 +81,17 @@ def rel_err(got, want):
   """max |got-want| / max|want| — the per-tensor relative error used for activations."""
   want = np.asarray(want, np.float64)
   return float(np.abs(np.asarray(got, np.float64) - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+def preprocess_gpu(img_u8, width, height, bgr_means, order, device=0):
+  """sqdet_preprocess_u8 on one uint8 [H0, W0, 3] image -> float32 [height, width, 3]."""
+  lib = _lib.load()
+  img = np.ascontiguousarray(img_u8, np.uint8)
+  h0, w0 = img.shape[:2]
+  src = DeviceBuffer.from_numpy(img, device)
+  dst = DeviceBuffer(height * width * 3 * 4, device)
+  means = np.ascontiguousarray(np.asarray(bgr_means, np.float64).reshape(3))
+  code = {'demo': 0, 'eval': 1}[order]
+  _lib.check(lib.sqdet_preprocess_u8(src.ptr, h0, w0, dst.ptr, height, width, means.ctypes.data,
+                                     code, None))
+  return dst.to_numpy(np.float32, (height, width, 3))

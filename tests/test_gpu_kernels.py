@@ -5,7 +5,7 @@ import pytest
 
 import oracle
 from squeezedet_b200 import _lib
-from gpu_util import (conv2d_gpu, maxpool_gpu, interpret_gpu, topk_nms_gpu, rel_err)
+from gpu_util import (conv2d_gpu, maxpool_gpu, interpret_gpu, topk_nms_gpu, preprocess_gpu, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -160,3 +160,29 @@ def test_util_nms_gpu_matches_reference_keep(postproc_kat, gpu_device):
   for c in postproc_kat['cases']:
     if 0 < len(c['nms_keep']) <= 512:
       assert util.nms(c['boxes'], c['probs'], c['nms_thresh']) == c['nms_keep'].tolist(), c['name']
+
+
+@pytest.mark.parametrize('order', ['demo', 'eval'])
+@pytest.mark.parametrize('h0,w0,h,w', [(370, 1224, 375, 1242), (375, 1242, 375, 1242),
+                                       (720, 1280, 375, 1242), (37, 41, 19, 23), (5, 7, 31, 3)])
+def test_preprocess_u8_resize_meansub(h0, w0, h, w, order, gpu_device):
+  """f-1: uint8 -> float32, cv2 INTER_LINEAR resize, mean subtraction in the reference's two
+  orders.  The kernel restates oracle/preproc.py operation for operation (the oracle is pinned to
+  cv2 within 3 float32 ulp of the pixel range, tests/test_oracle_preproc.py)."""
+  from oracle import preproc
+  means = np.array([103.939, 116.779, 123.68])
+  rng = np.random.default_rng(h0 + 3 * w)
+  img = rng.integers(0, 256, (h0, w0, 3), dtype=np.uint8)
+  want = preproc.preprocess(img, w, h, means, order)
+  got = preprocess_gpu(img, w, h, means, order)
+  assert got.shape == want.shape
+  ulp = float(np.spacing(np.float32(255.0)))
+  assert np.abs(got - want).max() <= 2 * ulp, float(np.abs(got - want).max())
+  cv2 = pytest.importorskip('cv2')
+  x = img.astype(np.float32)
+  if order == 'demo':
+    ref = (cv2.resize(x, (w, h)) - means.reshape(1, 1, 3)).astype(np.float32)
+  else:
+    x -= means.reshape(1, 1, 3)
+    ref = cv2.resize(x, (w, h))
+  assert np.abs(got - ref).max() <= 4 * ulp
