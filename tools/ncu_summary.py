@@ -53,7 +53,9 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'lts__t_sector_hit_rate.pct', 'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum',
+        'l1tex__m_xbar2l1tex_read_bytes.sum', 'l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
         'launch__grid_size', 'launch__block_size', 'sm__cycles_elapsed.max']
 
