@@ -184,3 +184,17 @@ def test_not_a_checkpoint(tmp_path):
     tfc.read_checkpoint(p)
   with pytest.raises(tfc.CheckpointError):
     tfc.read_checkpoint(str(tmp_path / 'missing'))
+
+
+def test_load_weights_file_dispatch(tmp_path):
+  w = {'conv1/kernels': np.ones((3, 3, 3, 4), np.float32), 'conv1/biases': np.zeros(4, np.float32)}
+  npz = str(tmp_path / 'w.npz')
+  ckpt.save_npz(npz, w)
+  np.testing.assert_array_equal(ckpt.load_weights_file(npz)['conv1/kernels'], w['conv1/kernels'])
+  np.testing.assert_array_equal(ckpt.load_weights_file(npz[:-4])['conv1/biases'], w['conv1/biases'])
+  prefix = str(tmp_path / 'model.ckpt-5')
+  ckpt.save_tf_checkpoint(prefix, w)
+  assert sorted(ckpt.load_weights_file(prefix)) == sorted(w)
+  assert sorted(ckpt.load_weights_file(prefix + '.index')) == sorted(w)
+  with pytest.raises(FileNotFoundError):
+    ckpt.load_weights_file(str(tmp_path / 'nothing-here'))
