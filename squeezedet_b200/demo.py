@@ -50,7 +50,7 @@ def build_model(demo_net, gpu, checkpoint):
   if checkpoint == 'synthetic':
     model.load_weights(synth.synthetic_weights(synth.model_param_specs(model), seed=0))
   else:
-    model.load_weights(ckpt.load_weights_file(checkpoint))
+    model.load_weights(ckpt.load_weights_file(checkpoint, names=model.param_names()))
   return mc, model
 
 

@@ -79,7 +79,7 @@ def eval_once(flags):
   if flags.checkpoint_path == 'synthetic':
     model.load_weights(synth.synthetic_weights(synth.model_param_specs(model), seed=0))
   else:
-    model.load_weights(ckpt.load_weights_file(flags.checkpoint_path))
+    model.load_weights(ckpt.load_weights_file(flags.checkpoint_path, names=model.param_names()))
 
   with open(os.path.join(flags.data_path, 'ImageSets', flags.image_set + '.txt')) as f:
     image_ids = [x.strip() for x in f.readlines()]

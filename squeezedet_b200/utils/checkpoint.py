@@ -23,14 +23,17 @@ def save_npz(path, weights):
   np.savez(path, **{k: np.asarray(v, dtype=np.float32) for k, v in weights.items()})
 
 
-def load_weights_file(path):
+def load_weights_file(path, names=None):
   """{variable name: ndarray} from whatever `--checkpoint` points at: an .npz, or the Saver path
-  of a TensorFlow checkpoint (``.../model.ckpt-87000``, as in reference src/demo.py:181-184)."""
+  of a TensorFlow checkpoint (``.../model.ckpt-87000``, as in reference src/demo.py:181-184).
+  `names` (e.g. ``model.param_names()``) restricts a TensorFlow checkpoint to the variables the
+  model restores, like ``Saver(model.model_params)`` does - the optimizer slots and counters
+  stored next to them are then neither read nor checksummed."""
   from . import tf_checkpoint
   if path.endswith('.npz'):
     return load_npz(path)
   if tf_checkpoint.checkpoint_kind(path):
-    return tf_checkpoint.read_checkpoint(path)
+    return tf_checkpoint.read_checkpoint(path, names=set(names) if names is not None else None)
   if os.path.exists(path + '.npz'):
     return load_npz(path + '.npz')
   raise FileNotFoundError('%s: no .npz archive and no TensorFlow checkpoint (V2 .index/.data or '
