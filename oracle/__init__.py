@@ -17,6 +17,9 @@ PARITY PINNING:
     no tests or golden vectors; the restatement follows the TF op semantics of
     SURVEY.md App. A and is cross-validated two ways (naive loops vs im2col-GEMM
     vs torch-CPU), nothing external pins it.
+  * pre-processing (``oracle.preproc``: cv2 float32 INTER_LINEAR resize + mean
+    subtraction, both reference orders): PINNED against the installed cv2, the
+    reference's own dependency for that step (tests/test_oracle_preproc.py).
 """
 
 from .semantics import (  # noqa: F401
