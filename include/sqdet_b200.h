@@ -166,8 +166,51 @@ int sqdet_set_bgr_means(sqdet_engine* e, const double bgr_means[3]);   /* mc.BGR
 int sqdet_submit(sqdet_engine* e, const void* images, int img_type, sqdet_det* dets,
                  int32_t* counts);
 int sqdet_wait(sqdet_engine* e);
+/* Variable-size frames in front of the path: B uint8 BGR frames exactly as
+ * cv2.imread returns them, frame i = [heights[i], widths[i], 3].  The engine does
+ * astype(float32) + cv2.resize(..., (mc.IMAGE_WIDTH, mc.IMAGE_HEIGHT)) (float32 INTER_LINEAR) +
+ * `- mc.BGR_MEANS` in the reference order `order` (SQDET_PRE_RESIZE_THEN_SUB: src/demo.py:187-190;
+ * SQDET_PRE_SUB_THEN_RESIZE: src/dataset/imdb.py:85-97) on the GPU, then the forward; same
+ * depth-2 pipelining and sqdet_wait contract as sqdet_submit.  rescale != 0 additionally divides
+ * every det box by (x_scale, y_scale) = (IMAGE_WIDTH / widths[i], IMAGE_HEIGHT / heights[i])
+ * BEFORE filter_prediction, i.e. the order of src/eval.py:80-87.                            */
+int sqdet_submit_frames(sqdet_engine* e, const uint8_t* const* frames,
+                        const int32_t* heights, const int32_t* widths, int order,
+                        int rescale, sqdet_det* dets, int32_t* counts);
+/* src/eval.py:83-84 for callers that resize on the host: xy_scales = B pairs (x_scale,
+ * y_scale), host memory; every later forward divides det_boxes[b,:,0::2] by x_scale and
+ * [b,:,1::2] by y_scale (float32, as numpy does) between interpret_output and
+ * filter_prediction, so det_boxes, the records and the NMS all live on the original image.
+ * NULL switches it off.  Synchronous (waits for in-flight forwards).                       */
+int sqdet_set_box_scale(sqdet_engine* e, const float* xy_scales);
 /* Kernel launches issued by one sqdet_forward (for accounting).                        */
 int sqdet_launches_per_forward(sqdet_engine* e);
+/* The engine's own compute stream (cudaStream_t as void*): sqdet_detect / sqdet_submit run on
+ * it; callers that order foreign work behind those calls record events on it.              */
+void* sqdet_engine_stream(sqdet_engine* e);
+
+/* ---- multi-GPU: the ONE collective of the path ---------------------------------------
+ * The reference is single-device (`tf.device('/gpu:{}')`, src/nets/squeezeDet.py:21); the
+ * path shards over the batch with no data-path exchange, and the only collective is an
+ * ncclAllGather of each rank's result blob
+ *     [batch * max_dets sqdet_det records][batch int32 counts]
+ * NCCL is bound at run time (dlopen of libnccl.so.2, or $SQDET_NCCL_LIB).
+ * sqdet_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId; the launcher distributes it
+ * (any host channel).  sqdet_comm_init: ncclCommInitRank on the engine's device (collective
+ * over all ranks) + the [nranks][blob] receive buffer.  sqdet_comm_attach: use a communicator
+ * the caller owns instead (ncclComm_t as void*).  sqdet_set_gather_in_forward(1): every
+ * sqdet_forward / sqdet_submit then ends with the all-gather on the SAME stream, captured in
+ * the forward's CUDA graph (no host code between filter and collective).  sqdet_allgather:
+ * the collective alone on `stream` (comm NULL = the attached one).  sqdet_gathered_dev: the
+ * receive buffer, rank-major.                                                              */
+int sqdet_comm_unique_id(void* id128);
+int sqdet_comm_init(sqdet_engine* e, int nranks, int rank, const void* id128);
+int sqdet_comm_attach(sqdet_engine* e, void* nccl_comm, int nranks, int rank);
+int sqdet_comm_destroy(sqdet_engine* e);
+int sqdet_set_gather_in_forward(sqdet_engine* e, int on);
+int sqdet_allgather(sqdet_engine* e, void* nccl_comm, void* stream);
+int sqdet_gathered_dev(sqdet_engine* e, void** gathered_dev, int64_t* bytes_per_rank,
+                       int32_t* nranks);
 
 /* ---- stage-isolated kernels (device pointers, asynchronous on `stream`) -------------
  * `device` must be current-capable; buffers must live on it.                           */
@@ -179,6 +222,16 @@ int sqdet_conv2d(const float* x_dev, const float* w_hwio_dev, const float* bias_
                  int B, int H, int W, int Cin, int Cout, int size, int stride,
                  int padding, int relu, int y_cstride, int y_coff, int math_mode,
                  void* stream);
+/* SqueezeDet._fire_layer (src/nets/squeezeDet.py:81-106; same in squeezeDetPlus.py) as ONE
+ * call: y[..., :E1] = relu(1x1_e1(q)+b), y[..., E1:] = relu(3x3_e3(q)+b), q = relu(1x1_s(x)+b).
+ * x [B,H,W,Cin], kernels HWIO, y [B,H,W,E1+E3].  With SQDET_MATH_TF32X3_TC and a shape the
+ * fused kernel takes (Cin % 32 == 0, S % 16 == 0, S <= 96, E % 16 == 0) this is ONE kernel
+ * launch and the squeeze tensor never leaves the SM; other shapes run squeeze and expand
+ * as separate launches.  Synchronises the stream (test / debug entry, not the hot path).    */
+int sqdet_fire(const float* x_dev, const float* w_sq_dev, const float* b_sq_dev,
+               const float* w_e1_dev, const float* b_e1_dev, const float* w_e3_dev,
+               const float* b_e3_dev, float* y_dev, int B, int H, int W, int Cin, int S,
+               int E1, int E3, int math_mode, void* stream);
 /* tf.nn.max_pool NHWC (src/nn_skeleton.py:580-583).                                   */
 int sqdet_maxpool_nhwc(const float* x_dev, float* y_dev, int B, int H, int W, int C,
                        int size, int stride, int padding, void* stream);

@@ -81,7 +81,19 @@ SIGNATURES = {
     'sqdet_set_bgr_means': (_i, [_vp, _vp]),
     'sqdet_submit': (_i, [_vp, _vp, _i, _vp, _vp]),
     'sqdet_wait': (_i, [_vp]),
+    'sqdet_submit_frames': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    'sqdet_set_box_scale': (_i, [_vp, _vp]),
     'sqdet_launches_per_forward': (_i, [_vp]),
+    'sqdet_engine_stream': (_vp, [_vp]),
+    'sqdet_comm_unique_id': (_i, [_vp]),
+    'sqdet_comm_init': (_i, [_vp, _i, _i, _vp]),
+    'sqdet_comm_attach': (_i, [_vp, _vp, _i, _i]),
+    'sqdet_comm_destroy': (_i, [_vp]),
+    'sqdet_set_gather_in_forward': (_i, [_vp, _i]),
+    'sqdet_allgather': (_i, [_vp, _vp, _vp]),
+    'sqdet_gathered_dev': (_i, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64),
+                                C.POINTER(C.c_int32)]),
+    'sqdet_fire': (_i, [_fp] * 8 + [_i] * 8 + [_vp]),
     'sqdet_conv2d': (_i, [_fp, _fp, _fp, _fp, _fp, _fp] + [_i] * 12 + [_vp]),
     'sqdet_maxpool_nhwc': (_i, [_fp, _fp] + [_i] * 7 + [_vp]),
     'sqdet_preprocess_u8': (_i, [_vp, _i, _i, _fp, _i, _i, _vp, _i, _vp]),
@@ -131,6 +143,13 @@ def pad_code(padding):
 
 def device_count():
   return load().sqdet_device_count()
+
+
+def comm_unique_id():
+  """128-byte ncclUniqueId (rank 0 calls this and shares the bytes with the other ranks)."""
+  buf = (C.c_char * 128)()
+  check(load().sqdet_comm_unique_id(buf))
+  return bytes(buf)
 
 
 # ---- small helpers for callers that keep buffers outside torch ---------------------------

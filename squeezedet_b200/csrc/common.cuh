@@ -73,6 +73,7 @@ int launch_interpret(const float* preds, const float* anchors, float* boxes, flo
                      int64_t* cls, int B, int grid_h, int grid_w, int K, int C,
                      int image_width, int image_height, float exp_thresh,
                      cudaStream_t stream);
+int launch_rescale_boxes(float* boxes, const float* scales_xy, int B, int A, cudaStream_t stream);
 int launch_topk_nms(const float* boxes, const float* probs, const int64_t* cls, int B,
                     int A, int classes, int top_n, float prob_thresh, float nms_thresh,
                     sqdet_det* dets, int32_t* counts, int max_dets, cudaStream_t stream);

@@ -254,11 +254,14 @@ int launch_conv_pool_simt(const float* x, const float* w, const float* bias, con
   if (smem > 232448) return fail(SQDET_ERR_UNSUPPORTED, "conv+pool: tile does not fit in smem");
 #define SQ_LAUNCH_CP(KS_, NT_, MINB_)                                                          \
   do {                                                                                         \
-    static bool attr_set = false;                                                              \
-    if (!attr_set) {                                                                           \
+    /* the opt-in is per device: remember which devices of this process already have it */    \
+    static unsigned long long attr_devs = 0ull;                                                \
+    int dev_ = 0;                                                                              \
+    SQ_CUDA(cudaGetDevice(&dev_));                                                             \
+    if (dev_ >= 64 || !((attr_devs >> dev_) & 1ull)) {                                         \
       SQ_CUDA(cudaFuncSetAttribute(conv_pool_simt_kernel<KS_, NT_, MINB_>,                     \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));      \
-      attr_set = true;                                                                         \
+      if (dev_ < 64) attr_devs |= 1ull << dev_;                                                \
     }                                                                                          \
     conv_pool_simt_kernel<KS_, NT_, MINB_><<<grid, NT_, smem, stream>>>(p);                    \
   } while (0)

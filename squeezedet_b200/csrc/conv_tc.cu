@@ -1503,10 +1503,12 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     rc = encode_w_map(&P.tmWs, im->d_w, row * 2, KC, P.two_cta ? N / 2 : 2 * N / P.cluster);
     if (rc) return rc;
   }
-  // opt in to the full 227 KB once for both instantiations (the attribute is per function,
-  // not per launch, so it must cover the largest plan)
-  static bool attr_set = false;
-  if (!attr_set) {
+  // opt in to the full 227 KB once per DEVICE for every instantiation (the attribute is per
+  // function and per device context, not per launch, so it must cover the largest plan)
+  static unsigned long long attr_devs = 0ull;
+  int attr_dev = 0;
+  SQ_CUDA(cudaGetDevice(&attr_dev));
+  if (attr_dev >= 64 || !((attr_devs >> attr_dev) & 1ull)) {
     SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, false, false>,
@@ -1517,7 +1519,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     SQ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
+    if (attr_dev < 64) attr_devs |= 1ull << attr_dev;
   }
   return 1;
 }

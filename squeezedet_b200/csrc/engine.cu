@@ -9,6 +9,7 @@
 // (tcgen05 3xTF32 implicit GEMM or fp32 SIMT), CUDA-graph capture of the whole forward,
 // and the fused post-processing.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -21,6 +22,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "fire_tc.cuh"
 
 namespace sqdet {
 
@@ -132,6 +134,20 @@ struct sqdet_engine {
   double bgr_means[3] = {103.939, 116.779, 123.68};   // config.py:72
   cudaStream_t own_stream = nullptr;
   std::vector<cudaEvent_t> prof_events;
+  // eval-order rescale (src/eval.py:83-84): det_boxes / (x_scale, y_scale) BEFORE the filter
+  float* d_scales = nullptr;      // [2 pipeline slots][B][2] device
+  int scale_slot = 0;             // half read by the forward being enqueued
+  bool rescale_on = false;
+  // variable-size uint8 frames (sqdet_submit_frames): one staging buffer per pipeline slot
+  uint8_t* d_frames[2] = {nullptr, nullptr};
+  size_t frames_cap[2] = {0, 0};
+  // multi-GPU: the ONE collective of the path, ncclAllGather of the result blob
+  void* comm = nullptr;           // ncclComm_t
+  bool comm_owned = false;
+  int comm_nranks = 0, comm_rank = 0;
+  uint8_t* d_gathered = nullptr;  // [nranks][blob_bytes]
+  size_t blob_bytes = 0;
+  bool gather_in_forward = false;
 };
 
 namespace sqdet {
@@ -280,15 +296,74 @@ static int run_op(sqdet_engine* e, const Op& op, const float* x_override, cudaSt
   return fail(SQDET_ERR_STATE, "unknown op kind");
 }
 
+// ---- NCCL, bound at run time (dlopen): the library must load on boxes without NCCL ----------
+// Prototypes restated from nccl.h (stable since NCCL 2.0); ncclUniqueId is passed BY VALUE.
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.handle) return SQDET_OK;
+  const char* env = getenv("SQDET_NCCL_LIB");
+  const char* cands[] = {env, "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* c : cands) {
+    if (!c || !*c) continue;
+    h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(SQDET_ERR_UNSUPPORTED, "NCCL not found (set SQDET_NCCL_LIB to libnccl.so.2)");
+  NcclApi a;
+  a.handle = h;
+  a.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+  a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather)
+    return fail(SQDET_ERR_UNSUPPORTED, "NCCL library lacks the expected entry points");
+  g_nccl = a;
+  return SQDET_OK;
+}
+static int nccl_fail(int r, const char* what) {
+  std::string m = std::string("NCCL error in ") + what + ": ";
+  m += g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "unknown";
+  return fail(SQDET_ERR_CUDA, m);
+}
+
+static int run_allgather(sqdet_engine* e, void* comm, cudaStream_t stream) {
+  if (!comm) return fail(SQDET_ERR_STATE, "sqdet_allgather: no communicator attached");
+  if (!e->d_gathered) return fail(SQDET_ERR_STATE, "sqdet_allgather: gather buffer missing");
+  // records and counts are ONE contiguous blob (sqdet_finalize): one collective per step
+  const int r = g_nccl.AllGather(e->d_dets, e->d_gathered, e->blob_bytes, /*ncclUint8*/ 1, comm,
+                                 stream);
+  if (r != 0) return nccl_fail(r, "ncclAllGather");
+  return SQDET_OK;
+}
+
 static int run_postproc(sqdet_engine* e, cudaStream_t stream) {
   const sqdet_config& c = e->cfg;
   int rc = launch_interpret(e->tensors[e->preds].dev, e->d_anchors, e->d_boxes, e->d_probs,
                             e->d_cls, c.batch_size, e->grid_h, e->grid_w, c.anchors_per_grid,
                             c.classes, c.image_width, c.image_height, c.exp_thresh, stream);
   if (rc) return rc;
-  return launch_topk_nms(e->d_boxes, e->d_probs, e->d_cls, c.batch_size, (int)e->num_anchors,
-                         c.classes, c.top_n_detection, c.prob_thresh, c.nms_thresh, e->d_dets,
-                         e->d_counts, e->max_dets, stream);
+  if (e->rescale_on) {
+    rc = launch_rescale_boxes(e->d_boxes, e->d_scales + (size_t)e->scale_slot * c.batch_size * 2,
+                              c.batch_size, (int)e->num_anchors, stream);
+    if (rc) return rc;
+  }
+  rc = launch_topk_nms(e->d_boxes, e->d_probs, e->d_cls, c.batch_size, (int)e->num_anchors,
+                       c.classes, c.top_n_detection, c.prob_thresh, c.nms_thresh, e->d_dets,
+                       e->d_counts, e->max_dets, stream);
+  if (rc) return rc;
+  if (e->gather_in_forward && e->comm) return run_allgather(e, e->comm, stream);
+  return SQDET_OK;
 }
 
 // Upload parameters and derive what the kernels consume (BN scale/shift, TC packs).
@@ -371,6 +446,7 @@ static int forward_impl(sqdet_engine* e, const float* images_dev, cudaStream_t s
   if (!guard.ok) return fail(SQDET_ERR_CUDA, "cannot select the engine's device");
   int rc = prepare_params(e);
   if (rc) return rc;
+  e->scale_slot = (e->d_in_slot[1] && images_dev == e->d_in_slot[1]) ? 1 : 0;
   const bool can_graph = e->use_graph && stream != nullptr;   // legacy stream cannot capture
   if (!can_graph) return enqueue_all(e, images_dev, stream);
   sqdet_engine::GraphEntry* hit = nullptr;
@@ -476,6 +552,11 @@ int sqdet_destroy(sqdet_engine* e) {
   }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  cudaFree(e->d_scales);
+  cudaFree(e->d_frames[0]);
+  cudaFree(e->d_frames[1]);
+  cudaFree(e->d_gathered);
+  if (e->comm && e->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   (void)cudaGetLastError();   // never leave a stale error for the next engine's launch checks
   delete e;
   return SQDET_OK;
@@ -949,6 +1030,11 @@ int sqdet_forward_profiled(sqdet_engine* e, const float* images_dev, void* strea
                         c.batch_size, e->grid_h, e->grid_w, c.anchors_per_grid, c.classes,
                         c.image_width, c.image_height, c.exp_thresh, stream);
   if (rc) return rc;
+  if (e->rescale_on) {
+    rc = launch_rescale_boxes(e->d_boxes, e->d_scales + (size_t)e->scale_slot * c.batch_size * 2,
+                              c.batch_size, (int)e->num_anchors, stream);
+    if (rc) return rc;
+  }
   SQ_CUDA(cudaEventRecord(e->prof_events[n - 1], stream));
   rc = launch_topk_nms(e->d_boxes, e->d_probs, e->d_cls, c.batch_size, (int)e->num_anchors,
                        c.classes, c.top_n_detection, c.prob_thresh, c.nms_thresh, e->d_dets,
@@ -1073,10 +1159,231 @@ int sqdet_wait(sqdet_engine* e) {
 
 int sqdet_launches_per_forward(sqdet_engine* e) {
   if (!e) return SQDET_ERR_INVALID_ARG;
-  int n = 2;   // interpret + filter
+  int n = 2 + (e->rescale_on ? 1 : 0);   // interpret [+ rescale] + filter (NCCL's own kernel not counted)
   for (const auto& op : e->ops) n += op.launches;
   return n;
 }
+
+
+// ---- eval-order rescale ---------------------------------------------------------------------------
+int sqdet_set_box_scale(sqdet_engine* e, const float* xy_scales) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_set_box_scale before sqdet_finalize");
+  DeviceGuard guard(e->device);
+  const bool on = xy_scales != nullptr;
+  if (on) {
+    const size_t n = (size_t)e->cfg.batch_size * 2;
+    for (size_t i = 0; i < n; ++i)
+      if (!(xy_scales[i] > 0.f)) return fail(SQDET_ERR_INVALID_ARG, "sqdet_set_box_scale: scales must be positive");
+    if (!e->d_scales) SQ_CUDA(cudaMalloc(&e->d_scales, sizeof(float) * n * 2));
+    // synchronous: no forward may be in flight while the table changes (both pipeline halves)
+    SQ_CUDA(cudaDeviceSynchronize());
+    SQ_CUDA(cudaMemcpy(e->d_scales, xy_scales, sizeof(float) * n, cudaMemcpyHostToDevice));
+    SQ_CUDA(cudaMemcpy(e->d_scales + n, xy_scales, sizeof(float) * n, cudaMemcpyHostToDevice));
+  }
+  if (on != e->rescale_on) {
+    e->rescale_on = on;
+    drop_graph(e);           // the captured forward has one kernel more / less
+  }
+  return SQDET_OK;
+}
+
+// ---- variable-size uint8 frames in front of the path --------------------------------
+int sqdet_submit_frames(sqdet_engine* e, const uint8_t* const* frames, const int32_t* heights,
+                        const int32_t* widths, int order, int rescale, sqdet_det* dets,
+                        int32_t* counts) {
+  if (!e || !frames || !heights || !widths)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_submit_frames: null argument");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_submit_frames before sqdet_finalize");
+  if (order != SQDET_PRE_RESIZE_THEN_SUB && order != SQDET_PRE_SUB_THEN_RESIZE)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_submit_frames: order must be 0 (demo) or 1 (eval)");
+  if (e->n_submitted - e->n_waited >= 2)
+    return fail(SQDET_ERR_STATE, "sqdet_submit_frames: two batches already in flight; call sqdet_wait");
+  DeviceGuard guard(e->device);
+  const sqdet_config& c = e->cfg;
+  const int B = c.batch_size;
+  size_t total = 0;
+  std::vector<size_t> off((size_t)B);
+  for (int i = 0; i < B; ++i) {
+    if (!frames[i] || heights[i] <= 0 || widths[i] <= 0)
+      return fail(SQDET_ERR_INVALID_ARG, "sqdet_submit_frames: empty frame");
+    off[(size_t)i] = total;
+    total += ((size_t)heights[i] * widths[i] * 3 + 255) & ~(size_t)255;
+  }
+  const int slot = (int)(e->n_submitted & 1);
+  const int64_t n_pix = (int64_t)B * c.image_height * c.image_width;
+  if (!e->copy_stream) {
+    SQ_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    e->d_in_slot[0] = e->tensors[0].dev;
+    SQ_CUDA(cudaMalloc(&e->d_in_slot[1], sizeof(float) * (size_t)n_pix * 3));
+    for (int k = 0; k < 2; ++k) {
+      SQ_CUDA(cudaEventCreateWithFlags(&e->ev_h2d[k], cudaEventDisableTiming));
+      SQ_CUDA(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t cs = e->copy_stream, ks = e->own_stream;
+  if (e->slot_used[slot]) SQ_CUDA(cudaStreamWaitEvent(cs, e->ev_done[slot], 0));
+  if (e->frames_cap[slot] < total) {
+    // growing the staging buffer: the slot's previous forward must be done with it
+    if (e->slot_used[slot]) SQ_CUDA(cudaEventSynchronize(e->ev_done[slot]));
+    cudaFree(e->d_frames[slot]);
+    e->d_frames[slot] = nullptr;
+    SQ_CUDA(cudaMalloc(&e->d_frames[slot], total));
+    e->frames_cap[slot] = total;
+  }
+  for (int i = 0; i < B; ++i)
+    SQ_CUDA(cudaMemcpyAsync(e->d_frames[slot] + off[(size_t)i], frames[i],
+                            (size_t)heights[i] * widths[i] * 3, cudaMemcpyHostToDevice, cs));
+  SQ_CUDA(cudaEventRecord(e->ev_h2d[slot], cs));
+  // eval order: boxes go back to each frame's own pixel grid before the filter (eval.py:80-87)
+  if (rescale) {
+    std::vector<float> sc((size_t)B * 2);
+    for (int i = 0; i < B; ++i) {
+      // eval.py:72-74 / imdb.py:93-95: x_scale = mc.IMAGE_WIDTH / orig_w (Python floats = double)
+      sc[(size_t)2 * i] = (float)((double)c.image_width / (double)widths[i]);
+      sc[(size_t)2 * i + 1] = (float)((double)c.image_height / (double)heights[i]);
+    }
+    if (!e->rescale_on) {
+      int rc = sqdet_set_box_scale(e, sc.data());      // first use: allocate + enable
+      if (rc) return rc;
+    }
+    // this slot's half of the table, in stream order behind the forward that last read it
+    SQ_CUDA(cudaMemcpyAsync(e->d_scales + (size_t)slot * B * 2, sc.data(), sizeof(float) * B * 2,
+                            cudaMemcpyHostToDevice, ks));
+  } else if (e->rescale_on) {
+    int rc = sqdet_set_box_scale(e, nullptr);
+    if (rc) return rc;
+  }
+  SQ_CUDA(cudaStreamWaitEvent(ks, e->ev_h2d[slot], 0));
+  const size_t img_floats = (size_t)c.image_height * c.image_width * 3;
+  for (int i = 0; i < B; ++i) {
+    int rc = launch_resize_meansub_u8(e->d_frames[slot] + off[(size_t)i], heights[i], widths[i],
+                                      e->d_in_slot[slot] + (size_t)i * img_floats, c.image_height,
+                                      c.image_width, e->bgr_means[0], e->bgr_means[1],
+                                      e->bgr_means[2], order == SQDET_PRE_SUB_THEN_RESIZE, ks);
+    if (rc) return rc;
+  }
+  int rc = forward_impl(e, e->d_in_slot[slot], ks);
+  if (rc) return rc;
+  if (dets)
+    SQ_CUDA(cudaMemcpyAsync(dets, e->d_dets, sizeof(sqdet_det) * (size_t)B * e->max_dets,
+                            cudaMemcpyDeviceToHost, ks));
+  if (counts)
+    SQ_CUDA(cudaMemcpyAsync(counts, e->d_counts, sizeof(int32_t) * (size_t)B,
+                            cudaMemcpyDeviceToHost, ks));
+  SQ_CUDA(cudaEventRecord(e->ev_done[slot], ks));
+  e->slot_used[slot] = true;
+  ++e->n_submitted;
+  return SQDET_OK;
+}
+
+// ---- multi-GPU: ONE all-gather of the filtered records ---------------------------------------------
+int sqdet_comm_unique_id(void* id128) {
+  if (!id128) return fail(SQDET_ERR_INVALID_ARG, "sqdet_comm_unique_id: null buffer");
+  int rc = nccl_load();
+  if (rc) return rc;
+  NcclId id;
+  const int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return nccl_fail(r, "ncclGetUniqueId");
+  memcpy(id128, id.internal, 128);
+  return SQDET_OK;
+}
+
+static int comm_buffers(sqdet_engine* e) {
+  e->blob_bytes = sizeof(sqdet_det) * (size_t)e->cfg.batch_size * e->max_dets +
+                  sizeof(int32_t) * (size_t)e->cfg.batch_size;
+  cudaFree(e->d_gathered);
+  e->d_gathered = nullptr;
+  SQ_CUDA(cudaMalloc(&e->d_gathered, e->blob_bytes * (size_t)e->comm_nranks));
+  SQ_CUDA(cudaMemset(e->d_gathered, 0, e->blob_bytes * (size_t)e->comm_nranks));
+  return SQDET_OK;
+}
+
+int sqdet_comm_init(sqdet_engine* e, int nranks, int rank, const void* id128) {
+  if (!e || !id128) return fail(SQDET_ERR_INVALID_ARG, "sqdet_comm_init: null argument");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_comm_init before sqdet_finalize");
+  if (nranks <= 0 || rank < 0 || rank >= nranks)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_comm_init: bad nranks/rank");
+  if (e->comm) return fail(SQDET_ERR_STATE, "sqdet_comm_init: a communicator is already attached");
+  int rc = nccl_load();
+  if (rc) return rc;
+  DeviceGuard guard(e->device);
+  if (!guard.ok) return fail(SQDET_ERR_CUDA, "cannot select the engine's device");
+  NcclId id;
+  memcpy(id.internal, id128, 128);
+  void* comm = nullptr;
+  const int r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+  if (r != 0) return nccl_fail(r, "ncclCommInitRank");
+  e->comm = comm;
+  e->comm_owned = true;
+  e->comm_nranks = nranks;
+  e->comm_rank = rank;
+  rc = comm_buffers(e);
+  if (rc) return rc;
+  // one eager collective so that channels / peer connections exist before any graph capture
+  rc = run_allgather(e, e->comm, e->own_stream);
+  if (rc) return rc;
+  SQ_CUDA(cudaStreamSynchronize(e->own_stream));
+  return SQDET_OK;
+}
+
+int sqdet_comm_attach(sqdet_engine* e, void* nccl_comm, int nranks, int rank) {
+  if (!e || !nccl_comm) return fail(SQDET_ERR_INVALID_ARG, "sqdet_comm_attach: null argument");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_comm_attach before sqdet_finalize");
+  if (nranks <= 0 || rank < 0 || rank >= nranks)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_comm_attach: bad nranks/rank");
+  if (e->comm) return fail(SQDET_ERR_STATE, "sqdet_comm_attach: a communicator is already attached");
+  int rc = nccl_load();
+  if (rc) return rc;
+  DeviceGuard guard(e->device);
+  e->comm = nccl_comm;
+  e->comm_owned = false;
+  e->comm_nranks = nranks;
+  e->comm_rank = rank;
+  return comm_buffers(e);
+}
+
+int sqdet_comm_destroy(sqdet_engine* e) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  DeviceGuard guard(e->device);
+  cudaDeviceSynchronize();
+  drop_graph(e);
+  if (e->comm && e->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  e->comm = nullptr;
+  e->comm_owned = false;
+  e->gather_in_forward = false;
+  cudaFree(e->d_gathered);
+  e->d_gathered = nullptr;
+  return SQDET_OK;
+}
+
+int sqdet_set_gather_in_forward(sqdet_engine* e, int on) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  if (on && !e->comm) return fail(SQDET_ERR_STATE, "sqdet_set_gather_in_forward: no communicator");
+  if ((on != 0) != e->gather_in_forward) {
+    e->gather_in_forward = on != 0;
+    drop_graph(e);
+  }
+  return SQDET_OK;
+}
+
+int sqdet_allgather(sqdet_engine* e, void* nccl_comm, void* stream) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  if (!e->finalized) return fail(SQDET_ERR_STATE, "sqdet_allgather before sqdet_finalize");
+  DeviceGuard guard(e->device);
+  return run_allgather(e, nccl_comm ? nccl_comm : e->comm, (cudaStream_t)stream);
+}
+
+int sqdet_gathered_dev(sqdet_engine* e, void** gathered, int64_t* bytes_per_rank, int32_t* nranks) {
+  if (!e) return fail(SQDET_ERR_INVALID_ARG, "null engine");
+  if (!e->d_gathered) return fail(SQDET_ERR_STATE, "sqdet_gathered_dev: no communicator attached");
+  if (gathered) *gathered = e->d_gathered;
+  if (bytes_per_rank) *bytes_per_rank = (int64_t)e->blob_bytes;
+  if (nranks) *nranks = e->comm_nranks;
+  return SQDET_OK;
+}
+
+void* sqdet_engine_stream(sqdet_engine* e) { return e ? (void*)e->own_stream : nullptr; }
 
 // ---- stage-isolated kernels ------------------------------------------------------------------
 int sqdet_conv2d(const float* x_dev, const float* w_hwio_dev, const float* bias_dev,
@@ -1097,6 +1404,42 @@ int sqdet_conv2d(const float* x_dev, const float* w_hwio_dev, const float* bias_
   a.y = y_dev; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.size = size;
   a.stride = stride; a.padding = padding; a.relu = relu; a.y_cstride = y_cstride; a.y_coff = y_coff;
   return launch_conv_simt(a, (cudaStream_t)stream);
+}
+
+
+/* SqueezeDet._fire_layer as ONE stage-isolated call (src/nets/squeezeDet.py:81-106). */
+int sqdet_fire(const float* x_dev, const float* w_sq_dev, const float* b_sq_dev,
+               const float* w_e1_dev, const float* b_e1_dev, const float* w_e3_dev,
+               const float* b_e3_dev, float* y_dev, int B, int H, int W, int Cin, int S, int E1,
+               int E3, int math_mode, void* stream_v) {
+  if (!x_dev || !w_sq_dev || !b_sq_dev || !w_e1_dev || !b_e1_dev || !w_e3_dev || !b_e3_dev || !y_dev)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_fire: null pointer");
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || S <= 0 || E1 <= 0 || E3 <= 0)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_fire: non-positive dimension");
+  if (math_mode != SQDET_MATH_FP32_SIMT && math_mode != SQDET_MATH_TF32X3_TC)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_fire: unknown math_mode");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (math_mode == SQDET_MATH_TF32X3_TC) {
+    int rc = fire_fused_oneshot(x_dev, w_sq_dev, b_sq_dev, w_e1_dev, b_e1_dev, w_e3_dev, b_e3_dev,
+                                y_dev, B, H, W, Cin, S, E1, E3, stream);
+    if (rc != 1) return rc < 0 ? rc : SQDET_OK;   // 1 = shape not taken by the fused kernel
+  }
+  // un-fused: squeeze tensor through HBM, then the two expand convs into the concat tensor
+  float* q = nullptr;
+  SQ_CUDA(cudaMalloc(&q, sizeof(float) * (size_t)B * H * W * S));
+  int rc = sqdet_conv2d(x_dev, w_sq_dev, b_sq_dev, nullptr, nullptr, q, B, H, W, Cin, S, 1, 1,
+                        SQDET_PAD_SAME, 1, S, 0, math_mode, stream_v);
+  if (!rc)
+    rc = sqdet_conv2d(q, w_e1_dev, b_e1_dev, nullptr, nullptr, y_dev, B, H, W, S, E1, 1, 1,
+                      SQDET_PAD_SAME, 1, E1 + E3, 0, math_mode, stream_v);
+  if (!rc)
+    rc = sqdet_conv2d(q, w_e3_dev, b_e3_dev, nullptr, nullptr, y_dev, B, H, W, S, E3, 3, 1,
+                      SQDET_PAD_SAME, 1, E1 + E3, E1, math_mode, stream_v);
+  cudaError_t ce = cudaStreamSynchronize(stream);
+  cudaFree(q);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return cuda_fail(ce, "sqdet_fire sync");
+  return SQDET_OK;
 }
 
 int sqdet_maxpool_nhwc(const float* x_dev, float* y_dev, int B, int H, int W, int C, int size,

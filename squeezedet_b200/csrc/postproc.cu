@@ -82,6 +82,22 @@ interpret_kernel(const float* __restrict__ preds, const float* __restrict__ anch
   cls[idx] = best_c;
 }
 
+// det_boxes[j, :, 0::2] /= x_scale; det_boxes[j, :, 1::2] /= y_scale  (reference src/eval.py:83-84):
+// the rescale of ALL boxes to the original image that the reference applies BEFORE
+// filter_prediction.  numpy divides the float32 array by the (weak) Python float in float32.
+__global__ void __launch_bounds__(256)
+rescale_boxes_kernel(float4* __restrict__ boxes, const float* __restrict__ scales, int A,
+                     long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int b = (int)(idx / A);
+  const float xs = __ldg(scales + 2 * b), ys = __ldg(scales + 2 * b + 1);
+  float4 v = boxes[idx];
+  v.x = __fdiv_rn(v.x, xs); v.z = __fdiv_rn(v.z, xs);
+  v.y = __fdiv_rn(v.y, ys); v.w = __fdiv_rn(v.w, ys);
+  boxes[idx] = v;
+}
+
 // ------------------------------------------------------------------------------------------
 constexpr int FT = 1024;          // threads of the filter CTA
 constexpr int FCAP = 1024;        // max candidates per image
@@ -377,6 +393,18 @@ int launch_interpret(const float* preds, const float* anchors, float* boxes, flo
       preds, anchors, boxes, probs, reinterpret_cast<long long*>(cls), B, A, K, C,
       (float)(image_width - 1.0), (float)(image_height - 1.0), exp_thresh, slope);
   SQ_CHECK_LAUNCH("interpret_kernel");
+  return SQDET_OK;
+}
+
+int launch_rescale_boxes(float* boxes, const float* scales_xy, int B, int A,
+                         cudaStream_t stream) {
+  if (B <= 0 || A <= 0) return fail(SQDET_ERR_INVALID_ARG, "rescale_boxes: non-positive dimension");
+  if (reinterpret_cast<uintptr_t>(boxes) & 15)
+    return fail(SQDET_ERR_INVALID_ARG, "rescale_boxes: boxes must be 16-byte aligned");
+  const long long total = (long long)B * A;
+  rescale_boxes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(boxes), scales_xy, A, total);
+  SQ_CHECK_LAUNCH("rescale_boxes_kernel");
   return SQDET_OK;
 }
 

@@ -62,9 +62,12 @@ def preprocess(im_bgr_u8, mc):
   return im, (im - mc.BGR_MEANS).astype(np.float32)
 
 
-def detect_and_draw(model, mc, im, input_image):
+def detect_and_draw(model, mc, im, frame_u8):
+  """`frame_u8`: the uint8 BGR frame as read; resize + mean subtraction (demo.py:187-190) run on
+  the GPU in front of the forward (sqdet_submit_frames, order = resize then subtract)."""
   from .utils.viz import CLASS_COLORS, draw_box
-  final_boxes, final_probs, final_class = model.detect_filtered([input_image])[0]
+  dets, counts = model.detect_frames([frame_u8], order='demo', rescale=False)
+  final_boxes, final_probs, final_class = model.records_to_lists(dets[0], int(counts[0]))
   keep = [i for i in range(len(final_probs)) if final_probs[i] > mc.PLOT_PROB_THRESH]
   final_boxes = [final_boxes[i] for i in keep]
   final_probs = [final_probs[i] for i in keep]
@@ -80,12 +83,16 @@ def image_demo(flags):
   import cv2
   mc, model = build_model(flags.demo_net, flags.gpu, flags.checkpoint)
   os.makedirs(flags.out_dir, exist_ok=True)
-  for f in glob.iglob(flags.input_path):
-    im, input_image = preprocess(cv2.imread(f), mc)
-    im, boxes, probs, classes = detect_and_draw(model, mc, im, input_image)
+  results = []
+  for f in sorted(glob.iglob(flags.input_path)):
+    frame = cv2.imread(f)
+    im = cv2.resize(frame.astype(np.float32, copy=False), (mc.IMAGE_WIDTH, mc.IMAGE_HEIGHT))
+    im, boxes, probs, classes = detect_and_draw(model, mc, im, frame)   # `im`: drawing canvas
     out_file_name = os.path.join(flags.out_dir, 'out_' + os.path.split(f)[1])
     cv2.imwrite(out_file_name, im)
     print('Image detection output saved to {}'.format(out_file_name))
+    results.append((f, boxes, probs, classes))
+  return results
 
 
 def video_demo(flags):
@@ -102,9 +109,10 @@ def video_demo(flags):
     if not ret:
       break
     frame = frame[500:-205, 239:-439, :]           # the reference's hard-coded crop (demo.py:91)
-    im, input_image = preprocess(frame, mc)
+    frame = np.ascontiguousarray(frame)
+    im = cv2.resize(frame.astype(np.float32, copy=False), (mc.IMAGE_WIDTH, mc.IMAGE_HEIGHT))
     t_reshape = time.time()
-    im, boxes, probs, classes = detect_and_draw(model, mc, im, input_image)
+    im, boxes, probs, classes = detect_and_draw(model, mc, im, frame)
     t_detect = time.time()
     cv2.imwrite(os.path.join(flags.out_dir, str(count).zfill(6) + '.jpg'), im)
     t_draw = time.time()

@@ -3,12 +3,16 @@
 (`eval_once`, lines 48-134), same flags: --dataset --data_path --image_set --eval_dir
 --checkpoint_path --run_once --net --gpu.
 
-Per image (reference eval.py:69-92): read (float32, minus BGR means, resize —
-src/dataset/imdb.py:85-97), ONE GPU pass for detect + filter_prediction, rescale boxes to the
-original image (eval.py:83-84), corner format + score into all_boxes[cls][image].  Then the
-KITTI detection files are written (src/dataset/kitti.py:100-127) and, when the reference's
-unmodified `evaluate_object` binary is present, it is invoked and its stats_*_ap.txt parsed.
-The TensorBoard summaries and the checkpoint-polling loop (eval.py:171-239) are not rebuilt.
+Per image, in the reference's order (eval.py:69-92): the uint8 frame goes to the GPU, where it
+is converted to float32, has the BGR means subtracted and is resized (src/dataset/imdb.py:85-97);
+forward; ALL det boxes are rescaled to the original image (eval.py:83-84) and only then
+filtered (filter_prediction + NMS on original-image coordinates, eval.py:86-87) - one
+`sqdet_submit_frames(..., order=eval, rescale=1)` call; corner format + score go into
+all_boxes[cls][image].  Then the KITTI detection files are written
+(src/dataset/kitti.py:100-127) and the reference's unmodified `evaluate_object` binary
+(built by tools/build_kitti_eval.sh) is invoked and its stats_*_ap.txt parsed
+(kitti.py:129-159).  The TensorBoard summaries and the checkpoint-polling loop
+(eval.py:171-239) are not rebuilt.
 """
 from __future__ import annotations
 
@@ -54,15 +58,27 @@ def read_image(path, mc):
 
 
 def detections_to_all_boxes(records, count, scale, num_classes):
-  """One image's filtered records -> per-class lists of [xmin, ymin, xmax, ymax, score], boxes
-  rescaled to the original image (eval.py:83-91)."""
+  """One image's filtered records -> per-class lists of [xmin, ymin, xmax, ymax, score]
+  (eval.py:89-91).  `scale` = (x_scale, y_scale) still to be divided out, or None when the
+  engine already rescaled the boxes before the filter (the reference order, eval.py:83-87).
+  count < 0 is the filter's overflow marker (PROB_THRESH branch above the record capacity)."""
+  from ._lib import SqdetError
+  if count < 0:
+    raise SqdetError(-6, 'more boxes above PROB_THRESH than the record capacity')
   out = [[] for _ in range(num_classes)]
-  x_scale, y_scale = scale
+  x_scale, y_scale = scale if scale is not None else (1.0, 1.0)
   for r in records[:count]:
-    box = np.array([r['cx'] / x_scale, r['cy'] / y_scale, r['w'] / x_scale, r['h'] / y_scale],
-                   dtype=np.float32)
+    if scale is None:
+      box = np.array([r['cx'], r['cy'], r['w'], r['h']], dtype=np.float32)
+    else:
+      box = np.array([r['cx'] / x_scale, r['cy'] / y_scale, r['w'] / x_scale, r['h'] / y_scale],
+                     dtype=np.float32)
     out[int(r['cls'])].append(bbox_transform(box) + [r['prob']])
   return out
+
+
+EVAL_TOOL = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'dataset', 'kitti-eval',
+                         'cpp', 'evaluate_object')   # built by tools/build_kitti_eval.sh
 
 
 def eval_once(flags):
@@ -88,14 +104,16 @@ def eval_once(flags):
   all_boxes = [[[] for _ in range(num_images)] for _ in range(mc.CLASSES)]
   _t = {'im_detect': Timer(), 'im_read': Timer(), 'misc': Timer()}
   for i, index in enumerate(image_ids):
+    import cv2
     _t['im_read'].tic()
-    image, scale = read_image(os.path.join(image_dir, index + '.png'), mc)
+    frame = cv2.imread(os.path.join(image_dir, index + '.png'))     # uint8 BGR, original size
     _t['im_read'].toc()
     _t['im_detect'].tic()
-    dets, counts = model.detect_records(image[None])       # detect + filter in one GPU pass
+    # imdb.py:85-97 pre-processing, forward, eval.py:83-84 rescale, filter: one GPU pass
+    dets, counts = model.detect_frames([frame], order='eval', rescale=True)
     _t['im_detect'].toc()
     _t['misc'].tic()
-    per_class = detections_to_all_boxes(dets[0], int(counts[0]), scale, mc.CLASSES)
+    per_class = detections_to_all_boxes(dets[0], int(counts[0]), None, mc.CLASSES)
     for c in range(mc.CLASSES):
       all_boxes[c][i] = per_class[c]
     _t['misc'].toc()
@@ -105,8 +123,8 @@ def eval_once(flags):
 
   det_dir = os.path.join(flags.eval_dir, 'detection_files_{:s}'.format('0'), 'data')
   result_dir = write_kitti_detections(det_dir, image_ids, mc.CLASS_NAMES, all_boxes)
-  tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'kitti-eval', 'cpp',
-                      'evaluate_object')
+  tool = EVAL_TOOL
+  aps = names = None
   if os.path.exists(tool):
     cmd = ' '.join([tool, os.path.join(flags.data_path, 'training'),
                     os.path.join(flags.data_path, 'ImageSets', flags.image_set + '.txt'),
@@ -118,7 +136,9 @@ def eval_once(flags):
       print('    {}: {:.3f}'.format(name, ap))
     print('    Mean average precision: {:.3f}'.format(float(np.mean(aps))))
   else:
-    print('KITTI scorer binary not found ({}); detection files are in {}'.format(tool, det_dir))
+    print('KITTI scorer binary not found ({}; build it with tools/build_kitti_eval.sh); '
+          'detection files are in {}'.format(tool, det_dir))
+  return all_boxes, aps, names
 
 
 def main(argv=None):

@@ -358,6 +358,88 @@ class ModelSkeleton:
     self.wait()
     return dets, counts
 
+  # ---- variable-size uint8 frames: pre-processing on the GPU (demo.py:187-190 / imdb.py:85-97) ----
+  def submit_frames(self, frames, dets_ptr, counts_ptr, order='demo', rescale=False):
+    """frames: list of B uint8 BGR arrays [h_i, w_i, 3] as cv2.imread returns them.  The engine
+    resizes (cv2 float32 INTER_LINEAR) to (mc.IMAGE_WIDTH, mc.IMAGE_HEIGHT) and subtracts
+    mc.BGR_MEANS in the reference order ('demo': resize then subtract, demo.py:187-190; 'eval':
+    subtract then resize, imdb.py:85-97).  rescale=True: boxes are divided by each frame's
+    (x_scale, y_scale) BEFORE filter_prediction, like eval.py:80-87.  Same wait() contract as
+    submit(); the frame arrays must stay alive until then."""
+    B = self.mc.BATCH_SIZE
+    if len(frames) != B:
+      raise ValueError('need %d frames, got %d' % (B, len(frames)))
+    arrs = []
+    for f in frames:
+      a = np.ascontiguousarray(np.asarray(f, dtype=np.uint8))
+      if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError('a frame must be uint8 [h, w, 3], got %r' % (a.shape,))
+      arrs.append(a)
+    ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+    hs = (C.c_int32 * B)(*[a.shape[0] for a in arrs])
+    ws = (C.c_int32 * B)(*[a.shape[1] for a in arrs])
+    code = {'demo': 0, 'eval': 1}[order]
+    self._frames_alive = arrs
+    _lib.check(self._lib.sqdet_submit_frames(self._engine, ptrs, hs, ws, code,
+                                             int(bool(rescale)), dets_ptr, counts_ptr))
+
+  def detect_frames(self, frames, order='demo', rescale=False):
+    """Synchronous convenience over submit_frames: -> (dets [B,max_dets], counts [B])."""
+    B = self.mc.BATCH_SIZE
+    dets = np.empty((B, self.max_dets), _lib.DET_DTYPE)
+    counts = np.empty((B,), np.int32)
+    self.submit_frames(frames, dets.ctypes.data, counts.ctypes.data, order, rescale)
+    self.wait()
+    return dets, counts
+
+  def set_box_scale(self, scales):
+    """eval.py:83-84 for host-resized inputs: `scales` = B (x_scale, y_scale) pairs, or None to
+    switch the rescale off.  Later forwards divide det_boxes by them before the filter."""
+    if scales is None:
+      _lib.check(self._lib.sqdet_set_box_scale(self._engine, None))
+      return
+    arr = np.ascontiguousarray(np.asarray(scales, dtype=np.float32).reshape(-1))
+    if arr.size != 2 * self.mc.BATCH_SIZE:
+      raise ValueError('need BATCH_SIZE (x_scale, y_scale) pairs')
+    _lib.check(self._lib.sqdet_set_box_scale(self._engine, arr.ctypes.data))
+
+  # ---- multi-GPU: the one all-gather of the filtered records (shard.py drives this) ------------
+  def comm_init(self, nranks, rank, unique_id, in_forward=True):
+    """ncclCommInitRank on this engine's device; `unique_id` = the 128 bytes rank 0 obtained
+    from _lib.comm_unique_id() and shared through any host channel.  in_forward=True makes
+    every forward end with the all-gather (captured in its CUDA graph)."""
+    buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+    _lib.check(self._lib.sqdet_comm_init(self._engine, int(nranks), int(rank), buf))
+    if in_forward:
+      _lib.check(self._lib.sqdet_set_gather_in_forward(self._engine, 1))
+
+  def set_gather_in_forward(self, on):
+    _lib.check(self._lib.sqdet_set_gather_in_forward(self._engine, int(bool(on))))
+
+  def allgather(self, stream=None):
+    _lib.check(self._lib.sqdet_allgather(self._engine, None, stream))
+
+  def gathered_device(self):
+    """(device pointer, bytes per rank, nranks) of the all-gather receive buffer."""
+    p, nb, nr = C.c_void_p(), C.c_int64(), C.c_int32()
+    _lib.check(self._lib.sqdet_gathered_dev(self._engine, C.byref(p), C.byref(nb), C.byref(nr)))
+    return p.value, int(nb.value), int(nr.value)
+
+  def read_gathered(self):
+    """Host copy of the receive buffer as [nranks, bytes_per_rank] uint8 (synchronous)."""
+    ptr, nb, nr = self.gathered_device()
+    out = np.empty((nr, nb), np.uint8)
+    _lib.check(self._lib.sqdet_stream_sync(self.gpu_id, self.engine_stream()))
+    _lib.check(self._lib.sqdet_memcpy_d2h(out.ctypes.data, ptr, out.nbytes, None))
+    _lib.check(self._lib.sqdet_stream_sync(self.gpu_id, None))
+    return out
+
+  def comm_destroy(self):
+    _lib.check(self._lib.sqdet_comm_destroy(self._engine))
+
+  def engine_stream(self):
+    return self._lib.sqdet_engine_stream(self._engine)
+
   @staticmethod
   def records_to_lists(dets, count):
     """One image's records -> the reference's filter_prediction return triple."""

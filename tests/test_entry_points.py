@@ -59,3 +59,61 @@ def test_draw_box_marks_pixels():
                cdict=viz.CLASS_COLORS)
   assert tuple(im[25, 30]) == (255.0, 191.0, 0.0)          # top-left corner, class colour
   assert im.sum() > 0
+
+
+def test_caffe_pkl_import_fills_batchnorm_like_the_reference():
+  """reference nn_skeleton.py:403-411: kernels from cw[conv], mean/var from cw[bn_*],
+  gamma/beta from cw[scale_*]; missing BN blobs fall back to the tf initialisers (1,0,0,1),
+  never to zeros."""
+  from squeezedet_b200.utils import checkpoint as ckpt
+
+  class P:
+    def __init__(self, name, shape):
+      self.name, self.shape = name, shape
+
+  class M:
+    model_params = [
+        P('conv1/kernels', (7, 7, 3, 4)), P('conv1/biases', (4,)),
+        P('conv1/gamma', (4,)), P('conv1/beta', (4,)), P('conv1/mean', (4,)), P('conv1/var', (4,)),
+        P('conv2_x/res2a/res2a_branch1/kernels', (1, 1, 4, 8)),
+        P('conv2_x/res2a/res2a_branch1/gamma', (8,)), P('conv2_x/res2a/res2a_branch1/beta', (8,)),
+        P('conv2_x/res2a/res2a_branch1/mean', (8,)), P('conv2_x/res2a/res2a_branch1/var', (8,)),
+        P('conv2_x/res2b/res2b_branch2/res2b_branch2a/kernels', (1, 1, 8, 2)),
+        P('conv2_x/res2b/res2b_branch2/res2b_branch2a/gamma', (2,)),
+        P('conv2_x/res2b/res2b_branch2/res2b_branch2a/var', (2,)),
+    ]
+
+  rng = np.random.default_rng(0)
+  blobs = {
+      'conv1': [rng.normal(size=(4, 3, 7, 7)), rng.normal(size=(4,))],
+      'bn_conv1': [rng.normal(size=(4,)), rng.uniform(0.5, 2, size=(4,))],
+      'scale_conv1': [rng.normal(size=(4,)), rng.normal(size=(4,))],
+      'res2a_branch1': [rng.normal(size=(8, 4, 1, 1))],
+      'bn2a_branch1': [rng.normal(size=(1, 8, 1, 1)), rng.uniform(0.5, 2, size=(8,))],
+      'scale2a_branch1': [rng.normal(size=(8,)), rng.normal(size=(8,))],
+      'res2b_branch2a': [rng.normal(size=(2, 8, 1, 1))],
+      # no bn2b_branch2a / scale2b_branch2a blobs
+  }
+  w = ckpt.from_caffe_pkl(None, M, blobs=blobs)
+  np.testing.assert_allclose(w['conv1/kernels'], np.transpose(blobs['conv1'][0], [2, 3, 1, 0]),
+                             rtol=1e-6)
+  np.testing.assert_allclose(w['conv1/mean'], blobs['bn_conv1'][0], rtol=1e-6)
+  np.testing.assert_allclose(w['conv1/var'], blobs['bn_conv1'][1], rtol=1e-6)
+  np.testing.assert_allclose(w['conv1/gamma'], blobs['scale_conv1'][0], rtol=1e-6)
+  np.testing.assert_allclose(w['conv1/beta'], blobs['scale_conv1'][1], rtol=1e-6)
+  np.testing.assert_allclose(w['conv2_x/res2a/res2a_branch1/mean'],
+                             blobs['bn2a_branch1'][0].reshape(-1), rtol=1e-6)
+  assert ckpt.caffe_bn_names('res4f_branch2c') == ('bn4f_branch2c', 'scale4f_branch2c')
+  g = w['conv2_x/res2b/res2b_branch2/res2b_branch2a/gamma']
+  v = w['conv2_x/res2b/res2b_branch2/res2b_branch2a/var']
+  assert np.all(g == 1.0) and np.all(v == 1.0)
+
+
+def test_all_boxes_rejects_overflow_marker():
+  import pytest
+  from squeezedet_b200._lib import SqdetError
+  recs = np.zeros(3, DET_DTYPE)
+  with pytest.raises(SqdetError):
+    sq_eval.detections_to_all_boxes(recs, -1, None, 3)
+  out = sq_eval.detections_to_all_boxes(recs, 0, None, 3)
+  assert out == [[], [], []]
