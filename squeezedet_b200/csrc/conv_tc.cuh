@@ -1,5 +1,6 @@
 // tcgen05 (5th-gen tensor core) convolution path: plans, weight packing, launchers.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -49,6 +50,15 @@ int launch_fire_expand_tc(const TcFirePlan& plan, const float* q_dev, float* y_d
                           cudaStream_t stream);
 void tc_conv_release(TcConvPlan* plan);
 void tc_fire_release(TcFirePlan* plan);
+
+// Tensor-map encoders shared by the tensor-core kernels: NHWC fp32 activation, box
+// {KC ch, box_w, box_h, 1}, 128B (KC=32) / 64B (KC=16) swizzle; packed weight rows [rows][KC], box
+// {KC, N}.  Return SQDET_OK or a negative status.
+int tc_encode_act_map(CUtensorMap* map, const float* x, int B, int H, int W, int C, int KC,
+                      int box_w, int box_h);
+int tc_encode_w_map(CUtensorMap* map, const float* w, int rows, int KC, int N);
+// a whole tensor as a 1-D array of floats, box = `box` floats (no swizzle)
+int tc_encode_flat_map(CUtensorMap* map, const float* x, long long n, int box);
 
 // Stage-isolated entry (sqdet_conv2d with SQDET_MATH_TF32X3_TC): plans, packs from device
 // weights, launches, and releases; synchronises the stream (test/debug path, not the hot path).

@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "fire_tc.cuh"
+#include "first_tc.cuh"
 
 namespace sqdet {
 
@@ -83,6 +84,7 @@ struct Op {
   int64_t flops = 0, params = 0, min_bytes = 0;
   int launches = 0;
   TcFirePlan tcfire;             // fused expand pair (valid when tcfire.enabled)
+  FirstTcPlan first_tc;          // first layer conv+pool on tcgen05 (valid when first_tc.enabled)
   bool skip = false;             // pool op whose work happens in the producer's epilogue
   int fused_pool_op = -1;        // index of the pool op fused into this conv / fire
   bool first_layer_fused = false;  // Cin=3 stride-2 conv + 3x3/2 pool as one FFMA kernel
@@ -264,6 +266,7 @@ static int run_op(sqdet_engine* e, const Op& op, const float* x_override, cudaSt
         const Op& po = e->ops[op.fused_pool_op];
         const Tensor& in = e->tensors[c.src];
         const float* x = (c.src == 0 && x_override) ? x_override : in.dev;
+        if (op.first_tc.enabled) return launch_first_tc(op.first_tc, x, stream);
         if (c.tc.enabled) return launch_conv_tc(c.tc, x, e->tensors[op.out].dev, stream);
         return launch_conv_pool_simt(x, e->params[c.p_kernel].dev,
                                      c.p_bias >= 0 ? e->params[c.p_bias].dev : nullptr, c.scale,
@@ -397,11 +400,21 @@ static int prepare_params(sqdet_engine* e) {
           int rc = tc_conv_set_affine(&c.tc, sc.data(), sh.data());
           if (rc) return rc;
         }
+        if (op.first_tc.enabled && &c == &op.convs[0]) {
+          int rc = first_tc_set_affine(&op.first_tc, sc.data(), sh.data());
+          if (rc) return rc;
+        }
       }
     }
   }
   // tensor-core weight packs
   for (auto& op : e->ops) {
+    if (op.first_tc.enabled) {
+      const ConvSpec& c = op.convs[0];
+      const float* bias = c.p_bias >= 0 ? e->params[c.p_bias].host.data() : nullptr;
+      int rc = first_tc_pack_weights(&op.first_tc, e->params[c.p_kernel].host.data(), bias);
+      if (rc) return rc;
+    }
     for (auto& c : op.convs) {
       if (!c.tc.enabled) continue;
       const float* bias = c.p_bias >= 0 ? e->params[c.p_bias].host.data() : nullptr;
@@ -537,6 +550,7 @@ int sqdet_destroy(sqdet_engine* e) {
       tc_conv_release(&c.tc);
     }
     tc_fire_release(&op.tcfire);
+    first_tc_release(&op.first_tc);
   }
   cudaFree(e->d_anchors);
   cudaFree(e->d_boxes);
@@ -852,6 +866,17 @@ int sqdet_finalize(sqdet_engine* e) {
       if (env_first_tc < 0) {
         const char* a = getenv("SQDET_TC_FIRST_POOL");
         env_first_tc = a ? atoi(a) : 0;
+      }
+      if (c.math_mode == SQDET_MATH_TF32X3_TC && op.first_layer_fused && !env_first_tc) {
+        // first layer on tcgen05, pooled-pixel-major with the pool as a max over accumulators
+        // (first_tc.cu); shapes it declines stay on the fused FFMA kernel
+        ConvSpec& cs = op.convs[0];
+        const Op& po = e->ops[op.fused_pool_op];
+        int rc = first_tc_plan(&op.first_tc, e->tensors[cs.src].B, e->tensors[cs.src].H,
+                               e->tensors[cs.src].W, cs.Cout, cs.size, cs.stride, cs.padding,
+                               cs.relu, cs.p_gamma >= 0, po.size, po.stride, po.padding,
+                               e->tensors[op.out].dev);
+        if (rc < 0) return rc;
       }
       if (c.math_mode == SQDET_MATH_TF32X3_TC && op.first_layer_fused && env_first_tc) {
         // tensor-core first layer (gather mode) with the pool in its epilogue.  Parity-green but
