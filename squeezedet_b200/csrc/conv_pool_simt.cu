@@ -56,6 +56,8 @@ struct ConvPoolParams {
 template <int KS, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 conv_pool_simt_kernel(const ConvPoolParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int PH = 2 * (CT_H - 1) + KS;          // input patch rows
   constexpr int PW = 2 * (CT_W - 1) + KS;          // input patch cols (pixels)
   constexpr int K = KS * KS * 3;
@@ -263,7 +265,8 @@ int launch_conv_pool_simt(const float* x, const float* w, const float* bias, con
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));      \
       if (dev_ < 64) attr_devs |= 1ull << dev_;                                                \
     }                                                                                          \
-    conv_pool_simt_kernel<KS_, NT_, MINB_><<<grid, NT_, smem, stream>>>(p);                    \
+    SQ_CUDA(launch_kernel(conv_pool_simt_kernel<KS_, NT_, MINB_>, grid, dim3(NT_), smem, stream, \
+                          p));                                                               \
   } while (0)
   if (ksize == 3 && threads <= 256) SQ_LAUNCH_CP(3, 256, 2);
   else if (ksize == 3) SQ_LAUNCH_CP(3, 384, 1);

@@ -205,6 +205,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   const uint32_t par_b = smem_b + (uint32_t)(reinterpret_cast<uint8_t*>(s_par) - smem);
   const uint32_t out_b = smem_b + (uint32_t)(s_out - smem);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work decomposition: a cluster of C CTAs walks "super-items" = C consecutive tiles of one
   // chunk in lockstep, so that every weight tile is fetched from L2 once per cluster and
@@ -248,6 +249,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   if (C > 1) cluster_sync_all();           // peers' barriers exist before anyone multicasts
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // prologue done (overlapped the previous kernel's tail under PDL): from here on global memory
+  pdl_wait();
 
   // Register re-balancing between the warpgroups (launch bound: 168/thread) happens at the top
   // of every role branch, so that ptxas sees one register budget per branch.
@@ -771,6 +774,8 @@ splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ y,
                      const float* __restrict__ bias, const float* __restrict__ scale,
                      const float* __restrict__ shift, long long npix, int cout, int pitch,
                      int ksplit, int y_cstride, int y_coff, int relu) {
+  pdl_trigger();
+  pdl_wait();
   const int c4n = cout / 4;
   const long long total = npix * c4n;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -1336,11 +1341,14 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
   if (prm.cluster <= 1) {
     // classic launch (no cluster attribute: keeps the non-cluster CTA->SM placement path)
     if (prm.gather)
-      conv_tc_kernel<32, false, true><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+      SQ_CUDA(launch_kernel(conv_tc_kernel<32, false, true>, im->grid, dim3(NUM_THREADS), im->smem_bytes,
+                            stream, prm));
     else if (im->KC == 32)
-      conv_tc_kernel<32, false, false><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+      SQ_CUDA(launch_kernel(conv_tc_kernel<32, false, false>, im->grid, dim3(NUM_THREADS), im->smem_bytes,
+                            stream, prm));
     else
-      conv_tc_kernel<16, false, false><<<im->grid, NUM_THREADS, im->smem_bytes, stream>>>(prm);
+      SQ_CUDA(launch_kernel(conv_tc_kernel<16, false, false>, im->grid, dim3(NUM_THREADS), im->smem_bytes,
+                            stream, prm));
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = im->grid;
@@ -1368,9 +1376,10 @@ static int launch_impl(const TcImpl* im, const float* x_dev, float* y_dev, cudaS
     const long long total = im->npix * (im->cout / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
-        im->d_scratch, im->y_final, im->d_bias, im->d_scale, im->d_shift, im->npix, im->cout,
-        im->pitch, im->ksplit, im->y_cstride_final, im->y_coff_final, im->relu_final);
+    SQ_CUDA(launch_kernel(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, stream,
+                          (const float*)im->d_scratch, im->y_final, (const float*)im->d_bias,
+                          (const float*)im->d_scale, (const float*)im->d_shift, im->npix, im->cout,
+                          im->pitch, im->ksplit, im->y_cstride_final, im->y_coff_final, im->relu_final));
     SQ_CHECK_LAUNCH("splitk_reduce_kernel");
   }
   if (debug) {

@@ -31,6 +31,10 @@ namespace sqdet {
 static thread_local std::string g_last_error;
 
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+static thread_local bool g_pdl_launch = false;
+void set_pdl_launch(bool on) { g_pdl_launch = on; }
+bool pdl_launch() { return g_pdl_launch; }
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
@@ -84,6 +88,7 @@ struct Op {
   int64_t flops = 0, params = 0, min_bytes = 0;
   int launches = 0;
   TcFirePlan tcfire;             // fused expand pair (valid when tcfire.enabled)
+  FusedFirePlan fused;           // whole fire module in one kernel (valid when fused.enabled)
   FirstTcPlan first_tc;          // first layer conv+pool on tcgen05 (valid when first_tc.enabled)
   bool skip = false;             // pool op whose work happens in the producer's epilogue
   int fused_pool_op = -1;        // index of the pool op fused into this conv / fire
@@ -275,6 +280,7 @@ static int run_op(sqdet_engine* e, const Op& op, const float* x_override, cudaSt
       }
       return run_conv(e, op.convs[0], x_override, stream);
     case OP_FIRE: {
+      if (op.fused.enabled) return launch_fused_fire(op.fused, stream);
       int rc = run_conv(e, op.convs[0], x_override, stream);
       if (rc) return rc;
       if (op.tcfire.enabled)
@@ -421,6 +427,18 @@ static int prepare_params(sqdet_engine* e) {
       int rc = tc_conv_pack_weights(&c.tc, e->params[c.p_kernel].host.data(), bias);
       if (rc) return rc;
     }
+    if (op.fused.enabled) {
+      const ConvSpec& sq = op.convs[0];
+      const ConvSpec& e1 = op.convs[1];
+      const ConvSpec& e3 = op.convs[2];
+      int rc = fused_fire_pack_weights(&op.fused, e->params[sq.p_kernel].host.data(),
+                                       e->params[sq.p_bias].host.data(),
+                                       e->params[e1.p_kernel].host.data(),
+                                       e->params[e1.p_bias].host.data(),
+                                       e->params[e3.p_kernel].host.data(),
+                                       e->params[e3.p_bias].host.data());
+      if (rc) return rc;
+    }
     if (op.tcfire.enabled) {
       const ConvSpec& e1 = op.convs[1];
       const ConvSpec& e3 = op.convs[2];
@@ -444,11 +462,26 @@ static void drop_graph(sqdet_engine* e) {
 }
 
 static int enqueue_all(sqdet_engine* e, const float* images_dev, cudaStream_t stream) {
-  for (const auto& op : e->ops) {
-    int rc = run_op(e, op, images_dev, stream);
-    if (rc) return rc;
+  // Programmatic dependent launch for every kernel after the first (whose input comes from a
+  // copy or from the caller): see common.cuh.  SQDET_PDL=0 switches it off.
+  static int env_pdl = -1;
+  if (env_pdl < 0) {
+    const char* a = getenv("SQDET_PDL");
+    env_pdl = a ? atoi(a) : 1;
   }
-  return run_postproc(e, stream);
+  int rc = SQDET_OK;
+  bool first = true;
+  for (const auto& op : e->ops) {
+    rc = run_op(e, op, images_dev, stream);
+    if (rc) break;
+    if (first && !op.skip) {
+      first = false;
+      set_pdl_launch(env_pdl != 0);
+    }
+  }
+  if (!rc) rc = run_postproc(e, stream);
+  set_pdl_launch(false);
+  return rc;
 }
 
 static int forward_impl(sqdet_engine* e, const float* images_dev, cudaStream_t stream) {
@@ -550,6 +583,7 @@ int sqdet_destroy(sqdet_engine* e) {
       tc_conv_release(&c.tc);
     }
     tc_fire_release(&op.tcfire);
+    fused_fire_release(&op.fused);
     first_tc_release(&op.first_tc);
   }
   cudaFree(e->d_anchors);
@@ -902,6 +936,35 @@ int sqdet_finalize(sqdet_engine* e) {
             return fail(SQDET_ERR_STATE, "pool fusion was promised but the conv plan declined");
         } else {
           ConvSpec& sq = op.convs[0];
+          // The whole module as ONE kernel (fire_tc.cu) where it is the faster plan - measured on
+          // SqueezeDet b=20 (profiles/r2_fused_fire.txt): the layers with a 16-channel squeeze and
+          // thousands of tiles (fire2/3: -30 % / -17 %); deeper layers need their expand weights
+          // streamed per tile and a 2x squeeze (two M tiles per halo), and lose to the squeeze
+          // launch + fused expand pair.  SQDET_FUSED_FIRE: 0 never, 1 this rule, 2 every shape the
+          // kernel takes, 3 every shape with >= 4 tiles per SM.
+          static int env_fused = -1;
+          if (env_fused < 0) {
+            const char* a = getenv("SQDET_FUSED_FIRE");
+            env_fused = a ? atoi(a) : 1;
+          }
+          if (env_fused && !pool_ptr && e->tensors[sq.src].dev != nullptr && sq.src != 0) {
+            const Tensor& xin = e->tensors[sq.src];
+            int sms = 148, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const long long tiles = (long long)xin.B * ((xin.H + 15) / 16) * ((xin.W + 7) / 8);
+            if (env_fused == 2 || (tiles >= 4LL * sms && (env_fused == 3 || sq.Cout <= 16))) {
+              int rcf = fused_fire_plan(&op.fused, xin.B, xin.H, xin.W, xin.C, sq.Cout,
+                                        op.convs[1].Cout, op.convs[2].Cout, xin.dev,
+                                        e->tensors[op.out].dev);
+              if (rcf < 0) return rcf;
+            }
+          }
+          if (op.fused.enabled) {
+            op.launches = 1;
+            op.min_bytes = bytes;
+            continue;
+          }
           int rc = tc_conv_plan(&sq.tc, e->tensors[sq.src].B, e->tensors[sq.src].H,
                                 e->tensors[sq.src].W, sq.Cin, sq.Cout, 1, 1, SQDET_PAD_SAME, 1,
                                 false, e->tensors[sq.dst].C, 0, e->tensors[sq.src].dev,

@@ -22,6 +22,8 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
 __global__ void __launch_bounds__(256)
 maxpool_vec4_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
                     int C4, int k, int stride, int pad_t, int pad_l, int Ho, int Wo) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)B * Ho * Wo * C4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -52,6 +54,8 @@ maxpool_vec4_kernel(const float* __restrict__ x, float* __restrict__ y, int B, i
 __global__ void __launch_bounds__(256)
 maxpool_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
                       int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)B * Ho * Wo * C;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -79,6 +83,8 @@ maxpool_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
 __global__ void __launch_bounds__(256)
 add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b,
                 float* __restrict__ y, long long n4, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) {
     const float4 p = ld_stream(reinterpret_cast<const float4*>(a) + i);
@@ -222,11 +228,11 @@ int launch_maxpool(const float* x, float* y, int B, int H, int W, int C, int siz
   const long long cap = 148LL * 8 * 16;   // grid-stride beyond 16 waves of 8 CTAs/SM
   if (blocks > cap) blocks = cap;
   if (vec)
-    maxpool_vec4_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
-        x, y, B, H, W, C / 4, size, stride, gh.pad_before, gw.pad_before, gh.out, gw.out);
+    SQ_CUDA(launch_kernel(maxpool_vec4_kernel, dim3((unsigned)blocks), dim3(256), 0, stream,
+                          x, y, B, H, W, C / 4, size, stride, gh.pad_before, gw.pad_before, gh.out, gw.out));
   else
-    maxpool_scalar_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
-        x, y, B, H, W, C, size, stride, gh.pad_before, gw.pad_before, gh.out, gw.out);
+    SQ_CUDA(launch_kernel(maxpool_scalar_kernel, dim3((unsigned)blocks), dim3(256), 0, stream,
+                          x, y, B, H, W, C, size, stride, gh.pad_before, gw.pad_before, gh.out, gw.out));
   SQ_CHECK_LAUNCH("maxpool_kernel");
   return SQDET_OK;
 }
@@ -237,7 +243,7 @@ int launch_add_relu(const float* a, const float* b, float* y, int64_t n, cudaStr
                           reinterpret_cast<uintptr_t>(y)) & 15) == 0);
   const long long n4 = aligned ? n / 4 : 0;
   long long threads = n4 > 0 ? n4 : 1;
-  add_relu_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, b, y, n4, n);
+  SQ_CUDA(launch_kernel(add_relu_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream, a, b, y, n4, n));
   SQ_CHECK_LAUNCH("add_relu_kernel");
   return SQDET_OK;
 }

@@ -68,3 +68,21 @@ def test_fire_full_grid_and_border_padding(shape, gpu_device):
   # border rows / columns carry the padding effect: check them on their own scale
   for sl in (np.s_[:, 0], np.s_[:, -1], np.s_[:, :, 0], np.s_[:, :, -1]):
     assert rel_err(got[sl], want[sl]) < FIRE_RTOL
+
+
+@pytest.mark.parametrize('shape,spatial', [
+    (SQUEEZEDET_FIRES[0], (2, 94, 160)),     # S=16: resident expand weights, two Q buffers, 240 tiles
+    (SQUEEZEDET_FIRES[3], (8, 24, 78)),      # S=32: streamed weights, two Q buffers, 160 tiles
+    (SQUEEZEDET_FIRES[5], (8, 24, 78)),      # S=48: one Q buffer, three squeeze stages
+    (SQUEEZEDET_FIRES[7], (8, 24, 78)),      # S=64: one Q buffer, the whole tensor memory in use
+])
+def test_fire_persistent_grid_many_items(shape, spatial, gpu_device):
+  """More 16x8 tiles than SMs: every CTA of the single-kernel fire walks several items, so the Q
+  buffer hand-over (qfull / qempty), the squeeze-ahead order and the ring phases all wrap."""
+  args = make_case(shape, spatial, seed=5 + shape[1])
+  want = fire_oracle(*args, dtype=np.float64)
+  got = fire_gpu(*args, math_mode=_lib.MATH_TF32X3_TC, device=gpu_device)
+  assert not np.isnan(got).any()
+  assert rel_err(got, want) < FIRE_RTOL, rel_err(got, want)
+  again = fire_gpu(*args, math_mode=_lib.MATH_TF32X3_TC, device=gpu_device)
+  assert np.array_equal(got, again)            # deterministic: fixed summation order
