@@ -62,6 +62,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "halo_tc.cuh"
 #include "tc_ptx.cuh"
 
 namespace sqdet {
@@ -1600,6 +1601,17 @@ int tc_fire_pack_weights(TcFirePlan* plan, const float* w_e1, const float* b_e1,
   SQ_CUDA(cudaMemcpy(im->d_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
   SQ_CUDA(cudaMemcpy(im->d_bias, b_e1, sizeof(float) * plan->E1, cudaMemcpyHostToDevice));
   SQ_CUDA(cudaMemcpy(im->d_bias + plan->E1, b_e3, sizeof(float) * plan->E3, cudaMemcpyHostToDevice));
+  return SQDET_OK;
+}
+
+int launch_splitk_reduce(const float* part, float* y, const float* bias, const float* scale,
+                         const float* shift, long long npix, int cout, int pitch, int ksplit,
+                         int y_cstride, int y_coff, int relu, cudaStream_t stream) {
+  const long long total = npix * (cout / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  SQ_CUDA(launch_kernel(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, part, y, bias,
+                        scale, shift, npix, cout, pitch, ksplit, y_cstride, y_coff, relu));
   return SQDET_OK;
 }
 

@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "fire_tc.cuh"
+#include "halo_tc.cuh"
 #include "first_tc.cuh"
 
 namespace sqdet {
@@ -77,6 +78,7 @@ struct ConvSpec {
   float* scale = nullptr;      // device, BN only
   float* shift = nullptr;
   TcConvPlan tc;               // tensor-core plan (valid when tc.enabled)
+  HaloConvPlan halo;           // halo-tile 3x3 plan (valid when halo.enabled; then tc is not planned)
 };
 
 struct Op {
@@ -247,6 +249,7 @@ static int run_conv(sqdet_engine* e, const ConvSpec& c, const float* x_override,
   const Tensor& in = e->tensors[c.src];
   const Tensor& out = e->tensors[c.dst];
   const float* x = (c.src == 0 && x_override) ? x_override : in.dev;
+  if (c.halo.enabled) return launch_halo_conv(c.halo, stream);
   if (c.tc.enabled) return launch_conv_tc(c.tc, x, out.dev, stream);
   ConvArgs a;
   a.x = x;
@@ -406,6 +409,10 @@ static int prepare_params(sqdet_engine* e) {
           int rc = tc_conv_set_affine(&c.tc, sc.data(), sh.data());
           if (rc) return rc;
         }
+        if (c.halo.enabled) {
+          int rc = halo_conv_set_affine(&c.halo, sc.data(), sh.data());
+          if (rc) return rc;
+        }
         if (op.first_tc.enabled && &c == &op.convs[0]) {
           int rc = first_tc_set_affine(&op.first_tc, sc.data(), sh.data());
           if (rc) return rc;
@@ -422,8 +429,12 @@ static int prepare_params(sqdet_engine* e) {
       if (rc) return rc;
     }
     for (auto& c : op.convs) {
-      if (!c.tc.enabled) continue;
       const float* bias = c.p_bias >= 0 ? e->params[c.p_bias].host.data() : nullptr;
+      if (c.halo.enabled) {
+        int rc = halo_conv_pack_weights(&c.halo, e->params[c.p_kernel].host.data(), bias);
+        if (rc) return rc;
+      }
+      if (!c.tc.enabled) continue;
       int rc = tc_conv_pack_weights(&c.tc, e->params[c.p_kernel].host.data(), bias);
       if (rc) return rc;
     }
@@ -463,11 +474,13 @@ static void drop_graph(sqdet_engine* e) {
 
 static int enqueue_all(sqdet_engine* e, const float* images_dev, cudaStream_t stream) {
   // Programmatic dependent launch for every kernel after the first (whose input comes from a
-  // copy or from the caller): see common.cuh.  SQDET_PDL=0 switches it off.
+  // copy or from the caller): see common.cuh.  Opt-in (SQDET_PDL=1): measured on the captured
+  // forward graph it changes nothing (1.916 vs 1.912 ms/step, profiles/r2_pdl.txt) - the graph
+  // already removes the launch gaps and the kernels' prologues are ~2 us of a 1.9 ms step.
   static int env_pdl = -1;
   if (env_pdl < 0) {
     const char* a = getenv("SQDET_PDL");
-    env_pdl = a ? atoi(a) : 1;
+    env_pdl = a ? atoi(a) : 0;
   }
   int rc = SQDET_OK;
   bool first = true;
@@ -581,6 +594,7 @@ int sqdet_destroy(sqdet_engine* e) {
       if (c.scale) cudaFree(c.scale);
       if (c.shift) cudaFree(c.shift);
       tc_conv_release(&c.tc);
+      halo_conv_release(&c.halo);
     }
     tc_fire_release(&op.tcfire);
     fused_fire_release(&op.fused);
@@ -927,6 +941,33 @@ int sqdet_finalize(sqdet_engine* e) {
       if (c.math_mode == SQDET_MATH_TF32X3_TC && !op.first_layer_fused) {
         if (op.kind == OP_CONV) {
           ConvSpec& cs = op.convs[0];
+          // 3x3 stride-1 convs on the halo-tile kernel (halo_tc.cu) where operand staging bounded
+          // conv_tc.cu: few tiles per SM and a thin output (the ConvDet head).  SQDET_HALO_CONV:
+          // 0 never, 1 this rule, 2 every shape the kernel takes.
+          static int env_halo = -1;
+          if (env_halo < 0) {
+            const char* a = getenv("SQDET_HALO_CONV");
+            env_halo = a ? atoi(a) : 1;
+          }
+          if (env_halo && !pool_ptr && cs.size == 3 && cs.stride == 1 && cs.padding == SQDET_PAD_SAME &&
+              cs.src != 0) {
+            const Tensor& xin = e->tensors[cs.src];
+            int sms = 148, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const long long tiles = (long long)xin.B * ((xin.H + 7) / 8) * ((xin.W + 15) / 16);
+            if (env_halo >= 2 || (cs.Cout <= 128 && cs.Cin >= 256 && tiles < 8LL * sms)) {
+              int rch = halo_conv_plan(&cs.halo, xin.B, xin.H, xin.W, cs.Cin, cs.Cout, cs.relu,
+                                       cs.p_gamma >= 0, e->tensors[op.out].C, cs.y_coff, xin.dev,
+                                       e->tensors[op.out].dev);
+              if (rch < 0) return rch;
+            }
+          }
+          if (cs.halo.enabled) {
+            op.launches = cs.halo.launches;
+            op.min_bytes = bytes;
+            continue;
+          }
           int rc = tc_conv_plan(&cs.tc, e->tensors[cs.src].B, e->tensors[cs.src].H,
                                 e->tensors[cs.src].W, cs.Cin, cs.Cout, cs.size, cs.stride,
                                 cs.padding, cs.relu, cs.p_gamma >= 0, e->tensors[op.out].C,
@@ -1494,6 +1535,42 @@ int sqdet_conv2d(const float* x_dev, const float* w_hwio_dev, const float* bias_
   return launch_conv_simt(a, (cudaStream_t)stream);
 }
 
+
+int sqdet_conv3x3_halo(const float* x_dev, const float* w_hwio_dev, const float* bias_dev,
+                       const float* scale_dev, const float* shift_dev, float* y_dev, int B, int H,
+                       int W, int Cin, int Cout, int relu, int y_cstride, int y_coff, void* stream_v) {
+  if (!x_dev || !w_hwio_dev || !y_dev)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_conv3x3_halo: null pointer");
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0)
+    return fail(SQDET_ERR_INVALID_ARG, "sqdet_conv3x3_halo: non-positive dimension");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  HaloConvPlan plan;
+  int rc = halo_conv_plan(&plan, B, H, W, Cin, Cout, relu, scale_dev != nullptr, y_cstride, y_coff,
+                          x_dev, y_dev);
+  if (rc < 0) return rc;
+  if (rc == 0) return fail(SQDET_ERR_UNSUPPORTED, "sqdet_conv3x3_halo: shape not taken by the halo kernel");
+  std::vector<float> w((size_t)9 * Cin * Cout), b(Cout, 0.f), sc, sh;
+  cudaError_t ce = cudaMemcpy(w.data(), w_hwio_dev, w.size() * sizeof(float), cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess && bias_dev)
+    ce = cudaMemcpy(b.data(), bias_dev, Cout * sizeof(float), cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess && scale_dev) {
+    sc.resize(Cout); sh.resize(Cout);
+    ce = cudaMemcpy(sc.data(), scale_dev, Cout * sizeof(float), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(sh.data(), shift_dev, Cout * sizeof(float), cudaMemcpyDeviceToHost);
+  }
+  if (ce != cudaSuccess) {
+    halo_conv_release(&plan);
+    return cuda_fail(ce, "sqdet_conv3x3_halo: parameter download");
+  }
+  rc = halo_conv_pack_weights(&plan, w.data(), bias_dev ? b.data() : nullptr);
+  if (!rc && scale_dev) rc = halo_conv_set_affine(&plan, sc.data(), sh.data());
+  if (!rc) rc = launch_halo_conv(plan, stream);
+  ce = cudaStreamSynchronize(stream);
+  halo_conv_release(&plan);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return cuda_fail(ce, "sqdet_conv3x3_halo sync");
+  return SQDET_OK;
+}
 
 /* SqueezeDet._fire_layer as ONE stage-isolated call (src/nets/squeezeDet.py:81-106). */
 int sqdet_fire(const float* x_dev, const float* w_sq_dev, const float* b_sq_dev,

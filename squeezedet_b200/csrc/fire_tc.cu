@@ -722,7 +722,6 @@ int fused_fire_plan(FusedFirePlan* plan, int B, int H, int W, int Cin, int S, in
     if (a) P.bias_comp = (float)atof(a);
   }
   // shared-memory plan: the deepest configuration that fits 227 KB, in order of preference
-  const int budget = 232448 - 1024;
   const int fixed = FF_PAR_FLOATS * 4 + 1024 /*barriers*/;
   const bool can_reside = (long long)tiles * P.ew_tile <= 120 * 1024;
   struct Cand { int nq, nsq, nring, store_ring; };
@@ -742,10 +741,14 @@ int fused_fire_plan(FusedFirePlan* plan, int B, int H, int W, int Cin, int S, in
       if (force_nq && c.nq != force_nq) continue;
       if (force_nsq && c.nsq != force_nsq) continue;
       if (force_ring && !resident && c.nring != force_ring) continue;
-      const long long ew = resident ? (long long)tiles * P.ew_tile : (long long)c.nring * P.ew_tile;
-      const long long total = (long long)c.nq * P.q_bytes + (long long)c.nsq * P.sq_stage + ew +
-                              8LL * 4096 * c.store_ring + fixed + 2 * 1024 /*alignment slack*/;
-      if (total > budget) continue;
+      // the exact shared-memory map of this candidate (same arithmetic as below)
+      auto up1k = [](long long v) { return (v + 1023) & ~1023LL; };
+      long long off = up1k((long long)c.nsq * P.sq_stage);
+      off = up1k(off + (resident ? (long long)tiles : (long long)c.nring) * P.ew_tile);
+      off = up1k(off + 8LL * 4096 * c.store_ring);
+      off = up1k(off + (long long)c.nq * P.q_bytes);
+      off += fixed + 16 + 1024 /*base alignment*/;
+      if (off > 232448) continue;
       if (2 * S + 2 * Ne + 64 * c.nsq > 512) continue;
       P.nq = c.nq; P.nsq = c.nsq; P.nring = resident ? 1 : c.nring; P.store_ring = c.store_ring;
       P.resident = resident ? 1 : 0;

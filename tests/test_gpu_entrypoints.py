@@ -133,7 +133,13 @@ def test_eval_once_reference_order_files_and_scorer(tmp_path, gpu_device):
   if not os.path.exists(sq_eval.EVAL_TOOL):
     pytest.skip('scorer binary absent: __graft_entry__.build() compiles it where /root/reference exists')
   assert aps is not None and len(aps) == 3 * mc.CLASSES and names[0] == 'car_easy'
-  assert os.path.exists(tmp_path / 'eval' / 'detection_files_0' / 'stats_car_ap.txt')
+  # evaluate_object writes stats_<class>_ap.txt for exactly the classes that occur in the detection
+  # files (its eval_car / eval_pedestrian / eval_cyclist flags, evaluate_object.cpp:695-776)
+  res = tmp_path / 'eval' / 'detection_files_0'
+  for c, name in enumerate(mc.CLASS_NAMES):
+    has = any(len(all_boxes[c][i]) > 0 for i in range(len(ids)))
+    assert os.path.exists(res / ('stats_%s_ap.txt' % name)) == has, name
+  assert any(os.path.exists(res / ('stats_%s_ap.txt' % n)) for n in mc.CLASS_NAMES)
 
 
 def test_rescale_before_filter_changes_nothing_but_coordinates(gpu_device):

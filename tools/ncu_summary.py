@@ -6,14 +6,40 @@
   full <raw_page.csv> <out_prefix>          `ncu -i X.ncu-rep --page raw --csv` of one forward
                                             -> <out_prefix>_ncu_full.csv and <out_prefix>_traffic.json
 
-Launches are mapped to engine ops by their order inside one SqueezeDet forward."""
+Launches are mapped to engine ops by kernel name and order inside one SqueezeDet forward."""
 import csv, json, sys
 
-OPS = (['conv1+pool1'] + ['fire2.squeeze', 'fire2.expand', 'fire3.squeeze', 'fire3.expand', 'pool3',
-       'fire4.squeeze', 'fire4.expand', 'fire5.squeeze', 'fire5.expand', 'pool5'] +
-       [f'fire{i}.{p}' for i in range(6, 12) for p in ('squeeze', 'expand')] +
-       ['conv12.partials', 'conv12.reduce', 'interpret_output', 'filter_prediction'])
-N = len(OPS)   # 27 kernel launches per forward
+def ops_of(kernels):
+  """Engine op of each launch of ONE SqueezeDet forward, from the kernel names in launch order:
+  first_tc / conv_pool_simt = conv1+pool1; fire_fused = a whole fire module; conv_tc launches
+  alternate squeeze / expand inside the un-fused fire modules; the last conv_tc + splitk_reduce =
+  conv12; maxpool = pool3, pool5."""
+  ops, fire, half, pools = [], 2, 0, ['pool3', 'pool5']
+  n_tc_left = sum(1 for k in kernels if 'conv_tc_kernel' in k)
+  for k in kernels:
+    if 'first_tc_kernel' in k or 'conv_pool_simt' in k:
+      ops.append('conv1+pool1')
+    elif 'fire_fused_kernel' in k:
+      ops.append('fire%d.fused' % fire); fire += 1
+    elif 'maxpool' in k:
+      ops.append(pools.pop(0))
+    elif 'conv_tc_kernel' in k:
+      n_tc_left -= 1
+      if n_tc_left == 0 and fire > 11:
+        ops.append('conv12.partials')
+      else:
+        ops.append('fire%d.%s' % (fire, 'squeeze' if half == 0 else 'expand'))
+        half ^= 1
+        if half == 0: fire += 1
+    elif 'splitk_reduce' in k:
+      ops.append('conv12.reduce')
+    elif 'interpret' in k:
+      ops.append('interpret_output')
+    elif 'filter' in k:
+      ops.append('filter_prediction')
+    else:
+      ops.append(k.split('(')[0][-24:])
+  return ops
 
 def read_rows(path):
   rows = list(csv.reader(l for l in open(path) if not l.startswith('==')))
@@ -21,24 +47,26 @@ def read_rows(path):
   body = [r for r in rows[rows.index(hdr) + 1:] if len(r) == len(hdr)]
   return hdr, body
 
-def forward_start(names):
-  """index of the last complete forward: starts at a conv_pool_simt launch, ends at filter."""
-  starts = [i for i, n in enumerate(names) if 'conv_pool_simt' in n and i + N <= len(names)
-            and 'filter_kernel' in names[i + N - 1]]
-  if not starts:
-    raise SystemExit('no complete forward (%d launches) found' % N)
-  return starts[-1]
+def forward_span(names):
+  """(start, length) of the last complete forward: first-layer kernel ... filter_kernel."""
+  ends = [i for i, n in enumerate(names) if 'filter_kernel' in n]
+  for e in reversed(ends):
+    starts = [i for i in range(e) if 'first_tc_kernel' in names[i] or 'conv_pool_simt' in names[i]]
+    if starts:
+      return starts[-1], e - starts[-1] + 1
+  raise SystemExit('no complete forward found')
 
 def launches(path, prefix):
   hdr, body = read_rows(path)
   i_id, i_k, i_m, i_v = hdr.index('ID'), hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Value')
   dur = [(r[i_k], float(r[i_v].replace(',', ''))) for r in body if r[i_m] == 'gpu__time_duration.sum']
   names = [n for n, _ in dur]
-  s = forward_start(names)
+  s, N = forward_span(names)
   fw = dur[s:s + N]
+  OPS = ops_of([n for n, _ in fw])
   tot = sum(v for _, v in fw)
   with open(prefix + '_launch_shares.csv', 'w') as f:
-    f.write('# one forward (27 launches) out of the ncu launch list of `bench.py --steps 2 --warmup 1`\n')
+    f.write('# one forward (%d launches) out of the ncu launch list of `bench.py --steps 2 --warmup 1`\n' % N)
     f.write('# cold-cache, serialised under the profiler: compare SHARES, not absolutes\n')
     f.write('op,kernel,duration_us,share\n')
     for op, (n, v) in zip(OPS, fw):
@@ -66,7 +94,8 @@ def full(path, prefix):
   body = rows[2:]
   i_k = hdr.index('Kernel Name')
   names = [r[i_k] for r in body]
-  s = forward_start(names) if len(names) > N else 0
+  s, N = forward_span(names)
+  OPS = ops_of(names[s:s + N])
   cols = [(m, hdr.index(m)) for m in KEEP if m in hdr]
   def num(x):
     try: return float(x.replace(',', ''))
