@@ -941,13 +941,15 @@ int sqdet_finalize(sqdet_engine* e) {
       if (c.math_mode == SQDET_MATH_TF32X3_TC && !op.first_layer_fused) {
         if (op.kind == OP_CONV) {
           ConvSpec& cs = op.convs[0];
-          // 3x3 stride-1 convs on the halo-tile kernel (halo_tc.cu) where operand staging bounded
-          // conv_tc.cu: few tiles per SM and a thin output (the ConvDet head).  SQDET_HALO_CONV:
-          // 0 never, 1 this rule, 2 every shape the kernel takes.
+          // 3x3 stride-1 convs on the halo-tile kernel (halo_tc.cu): opt-in.  Measured
+          // (profiles/r2_halo_conv.txt): parity-green, 9x less TMA traffic, but every .ss MMA re-reads
+          // its 4 KB A tile from shared memory, which bounds a thin-N conv at ~86 clocks per MMA -
+          // ConvDet 0.339 vs 0.271 ms, VGG16 / ResNet-50 bodies +14 % / +3 %.  SQDET_HALO_CONV:
+          // 0 never (default), 1 thin heads with few tiles per SM (ConvDet), 2 every shape it takes.
           static int env_halo = -1;
           if (env_halo < 0) {
             const char* a = getenv("SQDET_HALO_CONV");
-            env_halo = a ? atoi(a) : 1;
+            env_halo = a ? atoi(a) : 0;
           }
           if (env_halo && !pool_ptr && cs.size == 3 && cs.stride == 1 && cs.padding == SQDET_PAD_SAME &&
               cs.src != 0) {

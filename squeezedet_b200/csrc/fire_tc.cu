@@ -19,15 +19,16 @@
 //             at start address + dy*160 + dx*16 (tools/desc_test.cu checks this on the hardware).
 //             The nine taps therefore need no im2col, no re-split and no TMA re-fetch: tcgen05.mma
 //             .ss form straight from the Q tile, B = packed hi/lo expand weights, resident in shared
-//             memory for the whole launch when they fit (fire2/3: 80 KB), else streamed tap by tap.
+//             memory for the whole launch when they fit (fire2/3: 80 KB), else streamed through a ring.
 //             (conv_tc.cu's expand kernel re-fetched and re-split the squeeze tile once per tap: its
 //             splitter, not the tensor pipe or HBM, bounded fire2-5.)
 //   epilogue: accumulator segments -> fp32 registers (+bias, ReLU) -> swizzled staging -> TMA store
 //             of {32 ch, 8 w, 4 h} boxes into the concat tensor.
-// Roles (640 threads): warpgroups 0,1 = drains (squeeze drain of M tile g; expand drain of the
-//   32-channel groups jg = g mod 2 of EVERY chunk), warpgroups 2,3 = operand splitters (alternate
-//   squeeze stages), warp 16 = TMA producer of the squeeze stages, warp 17 = TMEM owner + MMA
-//   issuer, warp 18 = TMA producer of the expand weights.
+// Roles (512 threads): warpgroups 0,1 = drains (squeeze drain of M tile g; expand drain of the
+//   32-channel groups jg = g mod 2 of EVERY chunk; 176 registers), warps 8-10 and 12-14 = the two
+//   operand splitter groups (alternate squeeze stages; only TMEM lanes 0..95 of a squeeze M tile hold
+//   pixels, which frees the fourth warp of each warpgroup), warp 11 = TMA producer of both rings,
+//   warp 15 = TMEM owner + MMA issuer.
 // Order: with two Q buffers the MMA warp issues squeeze(i+1) BEFORE expand(i), so the squeeze drain
 //   of the next item overlaps the expand MMAs of this one; with one buffer squeeze(i), expand(i).
 // Roofline: HBM-bound for fire2-5 (AI 24-60 FLOP/B); algorithmic bytes per pixel =
@@ -83,6 +84,7 @@ struct FireParams {
   int nchunks;
   int nsq, nq, nring;      // squeeze stages, Q buffers, expand-weight stages (resident: all tiles)
   int resident;
+  int sq_cat;              // squeeze MMAs as a_hi x [b_hi | b_lo] (N = 2S) + a_lo x b_hi: 2 per K step
   int ntiles_w;            // expand weight tiles in total
   int lo_rows_sq, lo_rows_e;   // rows between the hi and the lo copy in the packed matrices
   int tmem_cols;
@@ -201,7 +203,9 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
   pdl_wait();      // prologue overlapped the previous kernel's tail (PDL); global memory from here on
   // TMEM columns: [0, 2S) squeeze accumulators (M tile 0 | 1), [2S, 2S + 2Ne) expand accumulators
   // (two buffers), then one [a_hi | a_lo] = 64-column A slot per squeeze stage
-  const uint32_t col_e = (uint32_t)(2 * S), col_a = (uint32_t)(2 * S + 2 * Ne);
+  // (with sq_cat the squeeze accumulators are 2S wide: [hi x hi + lo x hi | hi x lo])
+  const int SW = p.sq_cat ? 2 * S : S;
+  const uint32_t col_e = (uint32_t)(2 * SW), col_a = (uint32_t)(2 * SW + 2 * Ne);
 
 #define FF_TILE_DECODE(item_)                          \
   int tile_ = (item_);                                 \
@@ -218,12 +222,8 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
    if ((warp & 3) == 3) {
     if (warp == 11) {
       // ================================ TMA producer ==========================================
-      // Both rings, in the MMA warp's consumption order (squeeze(s), then the expand weights of
-      // item s - look): a producer blocked on one ring is then always waiting for stages the MMA
-      // warp can reach with what has already been issued.
       if (lane == 0) {
         RingPos rq{0, 0u}, re{0, 0u};
-        const uint32_t w_sempty = 0, w_eempty = 0;
         const uint32_t bytes = (uint32_t)(FF_MT_ROWS * 128 + 2 * S * 128);
         const uint32_t half = (uint32_t)(Ne * KCE * 4);
         if (p.resident) {
@@ -285,15 +285,13 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
             }
           }
         }
-        if (p.dbg) {
-          p.dbg[blockIdx.x * 16 + 0] = w_sempty;
-          p.dbg[blockIdx.x * 16 + 1] = w_eempty;
-        }
       }
     } else {
       // ================================ MMA issuer (warp 15) ==================================
       const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_s2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * S) >> 3) << 17) |
+                                ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc_e = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Ne >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -317,7 +315,7 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
             FF_WAIT(w_sqempty, &sqempty[mt], (use & 1u) ^ 1u);
             if (mt) ++sq_use1; else ++sq_use0;
             tc_fence_after();
-            const uint32_t d_tmem = tmem_u + (uint32_t)(mt * S);
+            const uint32_t d_tmem = tmem_u + (uint32_t)(mt * SW);
             for (int kc = seg0; kc < kch && kc < seg0 + 3; ++kc) {
               FF_WAIT(w_split, &ssplit[rs.s], rs.ph);
               tc_fence_after();
@@ -330,9 +328,15 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
                 for (int j = 0; j < 4; ++j) {
                   const uint64_t dbh = dsw_hi | (uint64_t)(b_hi + 2 * j);
                   const uint64_t dbl = dsw_hi | (uint64_t)(b_lo + 2 * j);
-                  umma_tf32_ts(d_tmem, a_lo + 8 * j, dbh, idesc_s, (kc != seg0 || j != 0) ? 1u : 0u);
-                  umma_tf32_ts(d_tmem, a_hi + 8 * j, dbl, idesc_s, 1u);
-                  umma_tf32_ts(d_tmem, a_hi + 8 * j, dbh, idesc_s, 1u);
+                  if (p.sq_cat) {
+                    // the hi and lo weight tiles are adjacent rows of the stage: one N = 2S operand
+                    umma_tf32_ts(d_tmem, a_hi + 8 * j, dbh, idesc_s2, (kc != seg0 || j != 0) ? 1u : 0u);
+                    umma_tf32_ts(d_tmem, a_lo + 8 * j, dbh, idesc_s, 1u);
+                  } else {
+                    umma_tf32_ts(d_tmem, a_lo + 8 * j, dbh, idesc_s, (kc != seg0 || j != 0) ? 1u : 0u);
+                    umma_tf32_ts(d_tmem, a_hi + 8 * j, dbl, idesc_s, 1u);
+                    umma_tf32_ts(d_tmem, a_hi + 8 * j, dbh, idesc_s, 1u);
+                  }
                 }
                 umma_commit(&sempty[rs.s]);
               }
@@ -505,17 +509,24 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
         FF_WAIT(w_sqfull, &sqfull[g], sqn & 1u);
         tc_fence_after();
         const int nst = (kch - seg0) < 3 ? (kch - seg0) : 3;
-        const float gain = 1.f + p.bias_comp * (float)(12 * nst);
-        const uint32_t trow = tmem_base + lane_sel + (uint32_t)(g * S);
+        // chained MMAs per accumulator column in this segment: 3 per K step (sq_cat: 2 in the
+        // [hi x hi + lo x hi] half, 1 in the [hi x lo] half)
+        const float gain = 1.f + p.bias_comp * (float)((p.sq_cat ? 8 : 12) * nst);
+        const float gain2 = 1.f + p.bias_comp * (float)(4 * nst);
+        const uint32_t trow = tmem_base + lane_sel + (uint32_t)(g * SW);
 #pragma unroll
         for (int c0 = 0; c0 < FF_MAX_S; c0 += 16) {
           if (c0 < S) {                            // warp-uniform
-            uint32_t v[16];
+            uint32_t v[16], v2[16];
             tmem_ld16_nowait(trow + (uint32_t)c0, v);
+            if (p.sq_cat) tmem_ld16_nowait(trow + (uint32_t)(S + c0), v2);
             tmem_wait_ld();
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              acc[c0 + e] = fmaf(__uint_as_float(v[e]), gain, seg0 == 0 ? 0.f : acc[c0 + e]);
+            for (int e = 0; e < 16; ++e) {
+              float a = fmaf(__uint_as_float(v[e]), gain, seg0 == 0 ? 0.f : acc[c0 + e]);
+              if (p.sq_cat) a = fmaf(__uint_as_float(v2[e]), gain2, a);
+              acc[c0 + e] = a;
+            }
           }
         }
         tc_fence_before();
@@ -724,6 +735,10 @@ int fused_fire_plan(FusedFirePlan* plan, int B, int H, int W, int Cin, int S, in
   // shared-memory plan: the deepest configuration that fits 227 KB, in order of preference
   const int fixed = FF_PAR_FLOATS * 4 + 1024 /*barriers*/;
   const bool can_reside = (long long)tiles * P.ew_tile <= 120 * 1024;
+  // squeeze MMAs as 2 per K step (a_hi x [b_hi | b_lo] at N = 2S, a_lo x b_hi at N = S): opt-in, measured
+  // neutral to -3 % on fire2/3 (profiles/r2_fused_fire.txt) - the drains, not the MMA count, bound them
+  P.sq_cat = (S == 16 && env_int("SQDET_FF_SQCAT", 0)) ? 1 : 0;
+  const int SWh = P.sq_cat ? 2 * S : S;
   struct Cand { int nq, nsq, nring, store_ring; };
   // deepest squeeze ring first (measured: with 2-3 stages the MMA warp waits on the TMA -> splitter
   // latency at the start of every item), then two Q buffers, then the weight ring
@@ -749,7 +764,7 @@ int fused_fire_plan(FusedFirePlan* plan, int B, int H, int W, int Cin, int S, in
       off = up1k(off + (long long)c.nq * P.q_bytes);
       off += fixed + 16 + 1024 /*base alignment*/;
       if (off > 232448) continue;
-      if (2 * S + 2 * Ne + 64 * c.nsq > 512) continue;
+      if (2 * SWh + 2 * Ne + 64 * c.nsq > 512) continue;
       P.nq = c.nq; P.nsq = c.nsq; P.nring = resident ? 1 : c.nring; P.store_ring = c.store_ring;
       P.resident = resident ? 1 : 0;
       placed = true;
@@ -772,7 +787,7 @@ int fused_fire_plan(FusedFirePlan* plan, int B, int H, int W, int Cin, int S, in
   }
   {
     int cols = 32;
-    while (cols < 2 * S + 2 * Ne + 64 * P.nsq) cols <<= 1;
+    while (cols < 2 * SWh + 2 * Ne + 64 * P.nsq) cols <<= 1;
     P.tmem_cols = cols;
   }
   int dev = 0, sms = 148;

@@ -6,6 +6,7 @@
 // Roofline: HBM.  Algorithmic bytes = 4*(B*H*W*C + B*Ho*Wo*C); each input element is
 // read ~(k/stride)^2 times but the re-reads hit L1/L2 (adjacent threads share rows).
 #include <math_constants.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sqdet {
@@ -47,6 +48,53 @@ maxpool_vec4_kernel(const float* __restrict__ x, float* __restrict__ y, int B, i
         m.z = fmaxf(m.z, q.z); m.w = fmaxf(m.w, q.w);
       }
     }
+    reinterpret_cast<float4*>(y)[idx] = m;
+  }
+}
+
+// Stride-2 windows of 2x2 or 3x3 (every pool of the four nets): all K*K loads of a thread are
+// issued before the first max (addresses clamped into the image, out-of-image taps replaced by -inf
+// afterwards), 32-bit index arithmetic.  The generic kernel below branches around each tap, which
+// serialises its loads (pool3: 3.39 TB/s -> see profiles/r2_pool.txt).
+template <int K>
+__global__ void __launch_bounds__(256)
+maxpool_s2_vec4_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
+                       int C4, int pad_t, int pad_l, int Ho, int Wo) {
+  pdl_trigger();
+  pdl_wait();
+  const int total = B * Ho * Wo * C4;
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c4 = idx % C4;
+    int t = idx / C4;
+    const int ow = t % Wo;
+    t /= Wo;
+    const int oh = t % Ho;
+    const int n = t / Ho;
+    const int iy0 = oh * 2 - pad_t, ix0 = ow * 2 - pad_l;
+    const int base = n * H * W;
+    float4 q[K * K];
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      const int iy = min(max(iy0 + u, 0), H - 1);
+#pragma unroll
+      for (int v = 0; v < K; ++v) {
+        const int ix = min(max(ix0 + v, 0), W - 1);
+        q[u * K + v] = __ldg(x4 + (size_t)(base + iy * W + ix) * C4 + c4);
+      }
+    }
+    float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+#pragma unroll
+    for (int u = 0; u < K; ++u)
+#pragma unroll
+      for (int v = 0; v < K; ++v) {
+        const bool ok = (unsigned)(iy0 + u) < (unsigned)H && (unsigned)(ix0 + v) < (unsigned)W;
+        const float4 r = q[u * K + v];
+        if (ok) {
+          m.x = fmaxf(m.x, r.x); m.y = fmaxf(m.y, r.y);
+          m.z = fmaxf(m.z, r.z); m.w = fmaxf(m.w, r.w);
+        }
+      }
     reinterpret_cast<float4*>(y)[idx] = m;
   }
 }
@@ -227,7 +275,21 @@ int launch_maxpool(const float* x, float* y, int B, int H, int W, int C, int siz
   long long blocks = (total + 255) / 256;
   const long long cap = 148LL * 8 * 16;   // grid-stride beyond 16 waves of 8 CTAs/SM
   if (blocks > cap) blocks = cap;
-  if (vec)
+  static int env_fast = -1;
+  if (env_fast < 0) {
+    const char* a = getenv("SQDET_POOL_FAST");
+    env_fast = a ? atoi(a) : 1;
+  }
+  const long long in_elems = (long long)B * H * W * (C / 4);
+  if (vec && env_fast && stride == 2 && (size == 2 || size == 3) && total < (1LL << 30) &&
+      in_elems < (1LL << 30)) {
+    if (size == 3)
+      SQ_CUDA(launch_kernel(maxpool_s2_vec4_kernel<3>, dim3((unsigned)blocks), dim3(256), 0, stream, x, y,
+                            B, H, W, C / 4, gh.pad_before, gw.pad_before, gh.out, gw.out));
+    else
+      SQ_CUDA(launch_kernel(maxpool_s2_vec4_kernel<2>, dim3((unsigned)blocks), dim3(256), 0, stream, x, y,
+                            B, H, W, C / 4, gh.pad_before, gw.pad_before, gh.out, gw.out));
+  } else if (vec)
     SQ_CUDA(launch_kernel(maxpool_vec4_kernel, dim3((unsigned)blocks), dim3(256), 0, stream,
                           x, y, B, H, W, C / 4, size, stride, gh.pad_before, gw.pad_before, gh.out, gw.out));
   else

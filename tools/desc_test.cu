@@ -106,6 +106,23 @@ __global__ void __launch_bounds__(128, 1) k_rate(long long* out, int n, int row_
   if (threadIdx.x < 32) tmem_dealloc(tm, 256);
 }
 
+
+// Cost of the generic->async proxy fence a thread pays before a TMA store / an MMA may read what it
+// wrote with st.shared: 8 x st.shared.v4 followed by (mode 0) nothing, (1) fence.proxy.async,
+// (2) fence.proxy.async + __syncwarp, per iteration, one warp per SM sub-partition.
+__global__ void __launch_bounds__(128, 1) k_fence(long long* out, int mode, int iters) {
+  __shared__ __align__(1024) float buf[128 * 32];
+  const uint32_t a = smem_u32(buf) + threadIdx.x * 128;
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sts128(a + ((k ^ (threadIdx.x & 7)) << 4), make_float4(i, k, 0.f, 1.f));
+    if (mode >= 1) fence_async_proxy();
+    if (mode >= 2) __syncwarp();
+  }
+  if (threadIdx.x == 0) out[0] = clock64() - t0;
+}
+
 static float tf32(float x) {
   uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r;
 }
@@ -155,6 +172,19 @@ int main() {
         printf("mma_rate_ss N=%3d row_pitch %3d B chunk_pitch %4d B tap(%d,%d): %.1f clk/MMA\n", n, c[0], c[1],
                c[2], c[3], (double)h / 2000);
       }
+  }
+
+  {
+    long long* dt;
+    cudaMalloc(&dt, 8);
+    for (int mode = 0; mode < 3; ++mode) {
+      long long h = 0;
+      k_fence<<<1, 128>>>(dt, mode, 1000);
+      cudaDeviceSynchronize();
+      cudaMemcpy(&h, dt, 8, cudaMemcpyDeviceToHost);
+      printf("fence_cost mode %d (0 = 8 x st.shared.v4, 1 = + fence.proxy.async, 2 = + __syncwarp): %.1f clk/iteration\n",
+             mode, (double)h / 1000);
+    }
   }
   return 0;
 }
