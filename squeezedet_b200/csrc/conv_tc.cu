@@ -88,6 +88,8 @@ struct TcChunk {
   int bias_base;    // index of ch_base in the bias/scale/shift arrays
   int tap_begin;    // first filter tap of this chunk (split-K partials cover tap sub-ranges)
   int tap_count;    // number of taps (ksize*ksize unless split)
+  int kc_begin;     // first K chunk (of KC input channels) of this chunk; split-K partials cover ranges
+  int kc_count;     // number of K chunks (Cin / KC unless split)
 };
 
 struct TcParams {
@@ -126,6 +128,8 @@ struct TcParams {
   int two_cta;          // 1: CTA-pair MMA (cta_group::2), implies cluster == 2
   int cluster;          // CTAs per cluster (1, 2 or 4): weight tiles are TMA-multicast across it
   int exp_mode;         // timing experiments only (SQDET_TC_EXP): 1 no fence, 2 no store, 4 no STS
+  int two_split;        // 1: warpgroup 3 is a SECOND operand splitter (alternate stages) and warpgroup 2 the
+                        // only drain group: thin-N, K-heavy launches whose stage the splitter paced
   // static schedule (launches whose chunks differ in cost): sched[0 .. nbins] = first entry of each
   // cluster's item list, followed by the lists (longest-processing-time-first assignment);
   // null = round-robin `item = cluster id + k * clusters`
@@ -274,7 +278,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         tile /= p.tiles_w;
         const int h0 = (tile % p.tiles_h) * p.step_h - p.org_h, w0 = tw * p.step_w - p.org_w;
         const int img = tile / p.tiles_h;
-        const int iters = ck.tap_count * p.kch;
+        const int iters = ck.tap_count * ck.kc_count;
         const uint32_t a_bytes = (uint32_t)(p.ct_h * p.ct_w * KC * 4);   // the TMA box
         for (int i = 0; i < iters; ++i, ++it) {
           const int s = st_i;
@@ -289,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           mbar_expect_tx(&full[s], (GATHER ? (uint32_t)(p.g_ph * p.g_box * 4) : a_bytes) +
                                        (uint32_t)(2 * B_BYTES));
 #endif
-          const int tl = i / p.kch, kc = i - tl * p.kch;
+          const int tl = i / ck.kc_count, kc = ck.kc_begin + (i - tl * ck.kc_count);
           const int tap = ck.tap_begin + tl;
           const int dy = tap / ck.ksize, dx = tap - dy * ck.ksize;
 #ifdef SQDET_ABLATE
@@ -354,8 +358,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       long long w_split = 0, w_tempty = 0;
       SQ_FOR_ITEMS(, ++n_item) {
         const TcChunk ck = p.chunk[item / spc];
-        const int iters = ck.tap_count * p.kch;
-        const int owner = n_item & 1;                     // drain group of this item
+        const int iters = ck.tap_count * ck.kc_count;
+        const int owner = p.two_split ? 0 : (n_item & 1);   // drain group of this item
         for (int i0 = 0; i0 < iters; i0 += G, ++g) {
           const int buf = g & 1;
           SQ_TIMED_WAIT(w_tempty, &tempty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);   // buffer drained
@@ -412,21 +416,25 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
     }
    }   // warps 2-3 of warpgroup 0 are spare: straight to the teardown barrier
-  } else if (warp < 8) {
+  } else if (warp < 8 || (p.two_split && warp >= 12)) {
     // ================================ operand splitter ====================================
+    // (two_split: warpgroups 1 and 3 take alternate stages; BOTH wait on every full[s] in order - an
+    // mbarrier waiter that skips phases can mistake phase n-2 for phase n)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-    const int t = threadIdx.x - 128;   // 0..127
+    const int sgroup = warp >= 12 ? 1 : 0;
+    const int t = threadIdx.x & 127;   // 0..127
     int it = 0, st_i = 0;
     uint32_t st_ph = 0;
     long long w_full = 0;
     SQ_FOR_ITEMS() {
       const TcChunk ck = p.chunk[item / spc];
-      const int iters = ck.tap_count * p.kch;
+      const int iters = ck.tap_count * ck.kc_count;
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = st_i;
         const uint32_t ph = st_ph;
         if (++st_i == S) { st_i = 0; st_ph ^= 1u; }
         SQ_TIMED_WAIT(w_full, &full[s], ph);
+        if (p.two_split && (it & 1) != sgroup) continue;
         // row t of the raw tile (KC*4 bytes, swizzled 16-byte chunks) -> registers ->
         // a_hi / a_lo -> TMEM slot s, lane t (this warp owns lanes 32*(warp%4)..+31)
         if (KC == 32 && GATHER) {
@@ -517,13 +525,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         else mbar_arrive(&split[s]);
       }
     }
-    if (p.dbg && t == 0) p.dbg[blockIdx.x * 12 + 3] = w_full;
+    if (p.dbg && t == 0 && sgroup == 0) p.dbg[blockIdx.x * 12 + 3] = w_full;
   } else {
     // ============================ segment drain + epilogue ================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     // two drain groups (warps 8-11 and 12-15) take alternate items
-    const int dgroup = (warp >= 12) ? 1 : 0;
-    const int ngroups = 2;
+    const int dgroup = (warp >= 12) ? 1 : 0;     // (two_split: warpgroup 3 never gets here)
+    const int ngroups = p.two_split ? 1 : 2;
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                 // accumulator row = pixel within the tile
     const int tt = threadIdx.x - 256 - 128 * dgroup;   // 0..127 within the drain group
@@ -534,7 +542,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     uint32_t use0 = 0u, use1 = 0u;               // own segments seen per TMEM buffer
     SQ_FOR_ITEMS(, ++n_item) {
       const TcChunk ck = p.chunk[item / spc];
-      const int iters = ck.tap_count * p.kch;
+      const int iters = ck.tap_count * ck.kc_count;
       if ((n_item % ngroups) != dgroup) {
         g += (iters + G - 1) / G;                // segments of an item the other group drains
         continue;
@@ -825,6 +833,7 @@ static EncodeTiledFn get_encode() {
 struct ConvGroup {        // one conv reading the shared input; >= 1 chunks
   int ksize, Cout, y_coff, bias_base;
   int tap_begin = 0, tap_count = -1;   // tap sub-range (split-K); -1 = all ksize*ksize taps
+  int kc_begin = 0, kc_count = -1;     // input-channel chunk sub-range (split-K); -1 = all Cin / KC
 };
 
 struct TcImpl {
@@ -978,7 +987,9 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
       c.bias_base = g.bias_base + cb;
       c.tap_begin = g.tap_begin;
       c.tap_count = g.tap_count < 0 ? g.ksize * g.ksize : g.tap_count;
-      row += c.tap_count * kch * N;
+      c.kc_begin = g.kc_begin;
+      c.kc_count = g.kc_count < 0 ? kch : g.kc_count;
+      row += c.tap_count * c.kc_count * N;
       im->chunks.push_back(c);
     }
   }
@@ -1079,6 +1090,22 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
   }
   const bool two_cta = env_two != 0 && (N % 32 == 0) && P.ntiles >= 2;
   P.two_cta = two_cta ? 1 : 0;
+  {
+    // second splitter warpgroup instead of the second drain group: launches whose MMA stage
+    // (12 MMAs of N/2 clocks) is shorter than the splitter's ~650 clocks AND whose items are K-heavy
+    // (few epilogues per MMA: one drain group keeps up).  Measured (profiles/r2_two_split.txt): ConvDet
+    // 0.280 vs 0.271 ms, fire6/7 +5 %, VGG16 +18 % - the stage is a latency chain, not splitter throughput.
+    static int env_2s = -1;
+    if (env_2s < 0) {
+      const char* a = getenv("SQDET_TC_2SPLIT");
+      env_2s = a ? atoi(a) : 0;   // opt-in (2 = the rule below): measured slower everywhere it applies
+    }
+    int max_iters = 0;
+    for (auto& c : im->chunks)
+      max_iters = (c.tap_count * c.kc_count) > max_iters ? (c.tap_count * c.kc_count) : max_iters;
+    const bool want = env_2s == 1 || (env_2s == 2 && N <= 96 && max_iters >= 24);
+    P.two_split = (want && !two_cta && !pooled && !gs) ? 1 : 0;
+  }
   const size_t stage = (size_t)TILE_M * KC * 4 + (size_t)2 * (two_cta ? N / 2 : N) * KC * 4;
   // Pipeline depth and residency: with two CTAs per SM (<= ~110 KB each) there are two
   // independent TMA->split->MMA->drain pipelines per SM to hide latency; otherwise one deep one.
@@ -1169,14 +1196,14 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
     }
     bool differ = false;
     for (auto& c : im->chunks)
-      if (c.tap_count != im->chunks[0].tap_count) differ = true;
+      if (c.tap_count * c.kc_count != im->chunks[0].tap_count * im->chunks[0].kc_count) differ = true;
     // (only when a CTA gets few items: with dozens per CTA round-robin is already balanced, and
     // keeping a tile's 1x1 and 3x3 items adjacent in time is better for L2 - measured on fire2/3)
     if (env_lpt && differ && supers > nclusters && supers < 24 * nclusters) {
       const int spc_h = (P.ntiles + cluster - 1) / cluster;
       std::vector<int> order(im->chunks.size());
       for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-      auto cost_of = [&](int c) { return 2 * im->chunks[c].tap_count * kch + 3; };   // + epilogue
+      auto cost_of = [&](int c) { return 2 * im->chunks[c].tap_count * im->chunks[c].kc_count + 3; };   // + epilogue
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost_of(a) > cost_of(b); });
       typedef std::pair<long long, int> Bin;     // (load, cluster id): least loaded first
       std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> heap;
@@ -1276,7 +1303,7 @@ static int plan_common(TcImpl* im, int B, int H, int W, int Cin, const std::vect
 
 // Pack group `gi` weights (HWIO [k,k,Cin,Cout]) into the [chunk][tap][kchunk][N][KC] hi/lo rows.
 static void pack_group(const TcImpl* im, int gi, const float* w_hwio, std::vector<float>& packed) {
-  const int KC = im->KC, N = im->prm.N, kch = im->prm.kch, Cin = im->Cin;
+  const int KC = im->KC, N = im->prm.N, Cin = im->Cin;
   const ConvGroup& g = im->groups[gi];
   const size_t lo_off = (size_t)im->rows_half * KC;
   // chunks of this group appear in order; find the first
@@ -1285,10 +1312,10 @@ static void pack_group(const TcImpl* im, int gi, const float* w_hwio, std::vecto
   for (int cb = 0; cb < g.Cout; cb += N, ++ci) {
     const TcChunk& c = im->chunks[ci];
     for (int tl = 0; tl < c.tap_count; ++tl)
-      for (int kc = 0; kc < kch; ++kc)
+      for (int kc = c.kc_begin; kc < c.kc_begin + c.kc_count; ++kc)
         for (int n = 0; n < c.ch_count; ++n) {
           const int tap = c.tap_begin + tl;
-          const size_t rowi = (size_t)c.w_row_base + ((size_t)tl * kch + kc) * N + n;
+          const size_t rowi = (size_t)c.w_row_base + ((size_t)tl * c.kc_count + (kc - c.kc_begin)) * N + n;
           for (int k = 0; k < KC; ++k) {
             const float v = (kc * KC + k < Cin)
                                 ? w_hwio[((size_t)tap * Cin + (size_t)kc * KC + k) * g.Cout + cb + n]
@@ -1531,10 +1558,21 @@ int tc_conv_plan(TcConvPlan* plan, int B, int H, int W, int Cin, int Cout, int s
       delete im;
       return cuda_fail(ce, "cudaMalloc(split-K scratch)");
     }
+    static int env_rows = -1;
+    if (env_rows < 0) {
+      const char* a = getenv("SQDET_TC_SPLITK_ROWS");
+      env_rows = a ? atoi(a) : 0;
+    }
+    const int KCs = (Cin % 32 == 0) ? 32 : 16, kch_all = Cin / KCs;
     for (int s2 = 0; s2 < ksplit; ++s2) {
       ConvGroup g{size, Cout, s2 * pitch, 0};
-      g.tap_begin = s2 * size;           // one filter row per partial
-      g.tap_count = size;
+      if (env_rows || kch_all % ksplit != 0) {
+        g.tap_begin = s2 * size;         // one filter row per partial (reads the input ksplit times)
+        g.tap_count = size;
+      } else {
+        g.kc_begin = s2 * (kch_all / ksplit);   // one input-channel range per partial: every input
+        g.kc_count = kch_all / ksplit;          // byte is read once (ConvDet: 329 -> ~130 MB of DRAM reads)
+      }
       groups.push_back(g);
     }
     // partials: no bias / affine / relu in the conv epilogue (they are applied by the reduction)

@@ -20,7 +20,8 @@ CONV_CASES = [
     (2, 24, 31, 16, 64, 3, 1, 'SAME'),     # expand3x3, Cin=16
     (1, 13, 29, 48, 192, 3, 1, 'SAME'),    # fire6 expand (Cin=48)
     (1, 12, 20, 96, 384, 1, 1, 'SAME'),    # fire10 expand1x1
-    (1, 12, 20, 256, 72, 3, 1, 'SAME'),    # ConvDet head (N=72)
+    (1, 12, 20, 256, 72, 3, 1, 'SAME'),    # ConvDet head (N=72), split-K over filter rows (8 K chunks)
+    (1, 12, 20, 384, 72, 3, 1, 'SAME'),    # ConvDet head, split-K over input-channel ranges (12 K chunks)
     (1, 17, 23, 64, 128, 1, 2, 'SAME'),    # ResNet strided 1x1
     (1, 20, 20, 32, 32, 3, 1, 'SAME'),
     # first-layer gather mode (3x3 over 3 channels): every stride / padding / alignment class
