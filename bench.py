@@ -467,9 +467,12 @@ def run_ours(args):
     raise SystemExit('bench.py: no CUDA device visible; the engine has no CPU fallback')
   torch.cuda.set_device(local)
   if world > 1:
-    # stdout carries exactly one JSON line: keep NCCL's version banner off it
-    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-      os.environ['NCCL_DEBUG'] = 'WARN'
+    # stdout carries exactly one JSON line: NCCL prints its version banner (and everything else) to
+    # stdout at any NCCL_DEBUG level >= VERSION, so leave the level unset unless the caller asked for
+    # more, and send whatever it prints to stderr
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+      del os.environ['NCCL_DEBUG']
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     dist.init_process_group('nccl', rank=rank, world_size=world,
                             device_id=torch.device('cuda', local))
   stream = torch.cuda.Stream(device=local)

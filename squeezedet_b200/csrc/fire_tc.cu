@@ -84,6 +84,8 @@ struct FireParams {
   int nchunks;
   int nsq, nq, nring;      // squeeze stages, Q buffers, expand-weight stages (resident: all tiles)
   int resident;
+  int wg_perm;             // role of physical warpgroup i in bits [4i, 4i+4): 0,1 drains, 2 splitter A + TMA
+                           // producer, 3 splitter B + MMA issuer (issue arbitration favours high warp ids)
   int sq_cat;              // squeeze MMAs as a_hi x [b_hi | b_lo] (N = 2S) + a_lo x b_hi: 2 per K step
   int ntiles_w;            // expand weight tiles in total
   int lo_rows_sq, lo_rows_e;   // rows between the hi and the lo copy in the packed matrices
@@ -172,6 +174,8 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int role = (p.wg_perm >> (4 * (warp >> 2))) & 15;    // of this warpgroup, see FireParams
+  const bool ctl = (warp & 3) == 3;                          // fourth warp of a splitter warpgroup
   const int S = p.S, Ne = p.Ne;
   const int kch = p.Cin >> 5;                    // 32-channel K chunks of the squeeze
   const int ksq = S >> 3;                        // K steps of 8 squeeze channels (expand K per tap)
@@ -195,7 +199,7 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 15) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (role == 3 && ctl) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -215,12 +219,12 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
   const int img = tile_ / p.tiles_h;                   \
   const int h0 = th * FF_TH, w0 = tw * FF_TW;
 
-  if (warp >= 8) {
+  if (role >= 2) {
    // warpgroups 2 and 3: warps 8-10 / 12-14 = the two splitter groups (only TMEM lanes 0..95 of a
    // squeeze M tile hold pixels, so the fourth warp of each warpgroup is free for a control role)
    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-   if ((warp & 3) == 3) {
-    if (warp == 11) {
+   if (ctl) {
+    if (role == 2) {
       // ================================ TMA producer ==========================================
       if (lane == 0) {
         RingPos rq{0, 0u}, re{0, 0u};
@@ -432,7 +436,7 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
     }
    } else {
     // ================================ operand splitters =====================================
-    const int sg = (warp >= 12) ? 1 : 0;           // squeeze stages cnt with cnt % 2 == sg
+    const int sg = role - 2;                       // squeeze stages cnt with cnt % 2 == sg
     const int t = (warp & 3) * 32 + lane;          // row of the M tile = TMEM lane, 0..95
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     RingPos r{0, 0u};
@@ -477,13 +481,13 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
   } else {
     // ==================== drains: squeeze -> Q tile, expand -> output ========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
-    const int g = warp >> 2;                     // drain group: squeeze M tile g, expand groups jg % 2 == g
+    const int g = role;                          // drain group: squeeze M tile g, expand groups jg % 2 == g
     const int q = warp & 3;
     const int r = q * 32 + lane;                 // TMEM lane
     const int tt = threadIdx.x & 127;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     // epilogue parameters, the same for every item: squeeze bias, expand biases
-    for (int i = threadIdx.x; i < FF_PAR_FLOATS; i += 256) {
+    for (int i = g * 128 + tt; i < FF_PAR_FLOATS; i += 256) {
       float v = 0.f;
       if (i < FF_MAX_S) { if (i < S) v = __ldg(p.bias_sq + i); }
       else if (i - FF_MAX_S < p.E1 + p.E3) v = __ldg(p.bias_e + (i - FF_MAX_S));
@@ -645,7 +649,7 @@ fire_fused_kernel(const __grid_constant__ FireParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 15) {
+  if (role == 3 && ctl) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -727,6 +731,10 @@ int fused_fire_plan(FusedFirePlan* plan, int B, int H, int W, int Cin, int S, in
   P.q_half = (S / 4) * FF_QCH;
   P.q_bytes = 2 * P.q_half;
   P.sq_stage = FF_SQ_A + 2 * S * 128;
+  {
+    const char* a = getenv("SQDET_FF_PERM");
+    P.wg_perm = a ? (int)strtol(a, nullptr, 16) : 0x3210;
+  }
   P.bias_comp = 1.4e-8f;
   {
     const char* a = getenv("SQDET_TC_BIAS_COMP");

@@ -20,7 +20,9 @@ local = int(os.environ.get('LOCAL_RANK', rank))
 G = int(os.environ.get('GLOBAL_BATCH', '5'))
 W, H = 416, 128
 torch.cuda.set_device(local)
-dist.init_process_group('gloo', rank=rank, world_size=world)   # host channel for the NCCL id only
+# host channel for the engine communicator's 128-byte id and the final verdict: torch's own NCCL group
+# (gloo resolves the container hostname, which GPU boxes do not always resolve)
+dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', local))
 
 
 def make_model(batch):
@@ -54,7 +56,7 @@ if rank == 0:
   print('nccl_worker: world %d global batch %d byte-equal %s kept %d'
         % (world, G, ok, int(rc.sum())), flush=True)
 np.savez(os.path.join(os.environ['OUT_DIR'], 'rank%d.npz' % rank), dets=gd, counts=gc)
-flag = torch.tensor([1 if ok else 0])
+flag = torch.tensor([1 if ok else 0], device=torch.device('cuda', local))
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 model.comm_destroy()
 dist.destroy_process_group()
