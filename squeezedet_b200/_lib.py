@@ -191,6 +191,47 @@ class DeviceBuffer:
       pass
 
 
+class ScratchPool:
+  """Grow-only device scratch, one ONE allocation, reused call after call: the reference-style
+  two-step loop (`sess.run` then `model.filter_prediction`, demo.py:193-199) calls the stage-isolated
+  entries thousands of times, and five cudaMalloc/cudaFree pairs per call dominated them."""
+
+  def __init__(self, device=0):
+    self.device = device
+    self.buf = None
+
+  def carve(self, *sizes):
+    """-> device pointers of len(sizes) regions (256-byte aligned) inside the pooled allocation."""
+    offs, total = [], 0
+    for n in sizes:
+      offs.append(total)
+      total += (int(n) + 255) & ~255
+    if self.buf is None or self.buf.nbytes < total:
+      if self.buf is not None:
+        self.buf.free()
+      self.buf = DeviceBuffer(max(total, 1 << 16), self.device)
+    return [self.buf.ptr + o for o in offs]
+
+  def upload(self, ptr, arr):
+    arr = np.ascontiguousarray(arr)
+    check(load().sqdet_memcpy_h2d(ptr, arr.ctypes.data, arr.nbytes, None))
+
+  def download(self, ptr, dtype, shape):
+    out = np.empty(shape, dtype=dtype)
+    check(load().sqdet_memcpy_d2h(out.ctypes.data, ptr, out.nbytes, None))
+    check(load().sqdet_stream_sync(self.device, None))
+    return out
+
+
+_scratch_pools = {}
+
+
+def scratch_pool(device=0):
+  if device not in _scratch_pools:
+    _scratch_pools[device] = ScratchPool(device)
+  return _scratch_pools[device]
+
+
 class PinnedArray:
   """numpy view over cudaMallocHost memory (for the end-to-end host path)."""
 

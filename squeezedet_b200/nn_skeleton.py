@@ -539,20 +539,16 @@ class ModelSkeleton:
       return [], [], []
     topn = 0 < mc.TOP_N_DETECTION < n
     cap = int(mc.TOP_N_DETECTION) if topn else min(n, 1024)
-    dev = self.gpu_id
-    d_boxes = _lib.DeviceBuffer.from_numpy(boxes, dev)
-    d_probs = _lib.DeviceBuffer.from_numpy(probs, dev)
-    d_cls = _lib.DeviceBuffer.from_numpy(cls_idx, dev)
-    d_dets = _lib.DeviceBuffer(cap * _lib.DET_DTYPE.itemsize, dev)
-    d_cnt = _lib.DeviceBuffer(4, dev)
-    try:
-      _lib.check(self._lib.sqdet_topk_nms(
-          d_boxes.ptr, d_probs.ptr, d_cls.ptr, 1, n, int(mc.CLASSES),
-          int(mc.TOP_N_DETECTION), float(mc.PROB_THRESH), float(mc.NMS_THRESH),
-          d_dets.ptr, d_cnt.ptr, cap, None))
-      dets = d_dets.to_numpy(_lib.DET_DTYPE, (cap,))
-      count = int(d_cnt.to_numpy(np.int32, (1,))[0])
-    finally:
-      for b in (d_boxes, d_probs, d_cls, d_dets, d_cnt):
-        b.free()
+    # one pooled, grow-only scratch allocation instead of five cudaMalloc/cudaFree pairs per call
+    pool = _lib.scratch_pool(self.gpu_id)
+    p_boxes, p_probs, p_cls, p_dets, p_cnt = pool.carve(
+        boxes.nbytes, probs.nbytes, cls_idx.nbytes, cap * _lib.DET_DTYPE.itemsize, 4)
+    pool.upload(p_boxes, boxes)
+    pool.upload(p_probs, probs)
+    pool.upload(p_cls, cls_idx)
+    _lib.check(self._lib.sqdet_topk_nms(
+        p_boxes, p_probs, p_cls, 1, n, int(mc.CLASSES), int(mc.TOP_N_DETECTION),
+        float(mc.PROB_THRESH), float(mc.NMS_THRESH), p_dets, p_cnt, cap, None))
+    dets = pool.download(p_dets, _lib.DET_DTYPE, (cap,))
+    count = int(pool.download(p_cnt, np.int32, (1,))[0])
     return self.records_to_lists(dets, count)

@@ -67,20 +67,18 @@ def nms(boxes, probs, threshold, device=0):
     raise _lib.SqdetError(-3, 'nms: more than 1024 boxes in one call')
   lib = _lib.load()
   cls = np.zeros(n, np.int64)
-  bufs = [_lib.DeviceBuffer.from_numpy(a, device) for a in (boxes, probs, cls)]
-  d_dets = _lib.DeviceBuffer(n * _lib.DET_DTYPE.itemsize, device)
-  d_cnt = _lib.DeviceBuffer(4, device)
-  try:
-    # top_n = 0 selects the threshold branch; -inf threshold keeps every box as a
-    # candidate in original order, so only the NMS rule decides.
-    _lib.check(lib.sqdet_topk_nms(bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, 1, n, 1, 0,
-                                  C.c_float(-np.inf), C.c_float(threshold),
-                                  d_dets.ptr, d_cnt.ptr, n, None))
-    dets = d_dets.to_numpy(_lib.DET_DTYPE, (n,))
-    cnt = int(d_cnt.to_numpy(np.int32, (1,))[0])
-  finally:
-    for b in bufs + [d_dets, d_cnt]:
-      b.free()
+  pool = _lib.scratch_pool(device)       # pooled scratch: no cudaMalloc/cudaFree per call
+  p_boxes, p_probs, p_cls, p_dets, p_cnt = pool.carve(boxes.nbytes, probs.nbytes, cls.nbytes,
+                                                      n * _lib.DET_DTYPE.itemsize, 4)
+  pool.upload(p_boxes, boxes)
+  pool.upload(p_probs, probs)
+  pool.upload(p_cls, cls)
+  # top_n = 0 selects the threshold branch; -inf threshold keeps every box as a
+  # candidate in original order, so only the NMS rule decides.
+  _lib.check(lib.sqdet_topk_nms(p_boxes, p_probs, p_cls, 1, n, 1, 0, C.c_float(-np.inf),
+                                C.c_float(threshold), p_dets, p_cnt, n, None))
+  dets = pool.download(p_dets, _lib.DET_DTYPE, (n,))
+  cnt = int(pool.download(p_cnt, np.int32, (1,))[0])
   keep = [False] * n
   for a in dets['anchor'][:cnt]:
     keep[int(a)] = True

@@ -15,6 +15,19 @@ from squeezedet_b200 import _lib, nets, shard
 from squeezedet_b200 import config as cfg
 from squeezedet_b200.utils import synth
 
+import traceback
+
+
+def _excepthook(tp, val, tb):
+  # torchrun's summary hides the workers' own tracebacks: leave them where the test can read them
+  try:
+    with open(os.path.join(os.environ.get('OUT_DIR', '.'), 'err_rank%s.txt' % os.environ.get('RANK', '?')), 'w') as f:
+      traceback.print_exception(tp, val, tb, file=f)
+  finally:
+    traceback.print_exception(tp, val, tb)
+
+
+sys.excepthook = _excepthook
 rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
 local = int(os.environ.get('LOCAL_RANK', rank))
 G = int(os.environ.get('GLOBAL_BATCH', '5'))

@@ -49,7 +49,8 @@ def test_nccl_gather_in_graph_matches_single_rank(world, global_batch, tmp_path)
          '--nproc-per-node', str(world), '--master-addr', '127.0.0.1', '--master-port',
          str(port), os.path.join(ROOT, 'tests', 'nccl_worker.py')]
   r = subprocess.run(cmd, env=env, cwd=ROOT, timeout=600, capture_output=True, text=True)
-  assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+  errs = ''.join(open(tmp_path / f).read() for f in sorted(os.listdir(tmp_path)) if f.startswith('err_rank'))
+  assert r.returncode == 0, errs[-3000:] + r.stdout[-1000:] + r.stderr[-1000:]
   a = np.load(tmp_path / 'rank0.npz')
   b = np.load(tmp_path / 'rank1.npz')
   assert np.array_equal(a['dets'], b['dets']) and np.array_equal(a['counts'], b['counts'])
