@@ -11,6 +11,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+import oracle
 from squeezedet_b200 import _lib, nets, shard
 from squeezedet_b200 import config as cfg
 from squeezedet_b200.utils import synth
@@ -41,6 +42,8 @@ dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.dev
 def make_model(batch):
   mc = cfg.kitti_squeezeDet_config()
   mc.IMAGE_WIDTH, mc.IMAGE_HEIGHT, mc.BATCH_SIZE = W, H, batch
+  grid = oracle.layer_table('squeezeDet', H, W)[-1][2]      # ConvDet grid of this image size
+  mc.GRID_H, mc.GRID_W = grid[0], grid[1]
   mc.ANCHOR_BOX = cfg.set_anchors(mc)
   mc.ANCHORS = len(mc.ANCHOR_BOX)
   m = nets.SqueezeDet(mc, local)
